@@ -1,0 +1,387 @@
+// chol_abi.cu — the C ABI of libchol_b200.so (see include/chol_b200.h for the contract and
+// the reference interfaces each entry point replaces).  Host code here only validates
+// arguments and enqueues kernels; there is no CPU arithmetic and no CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "aux.cuh"
+#include "batched.cuh"
+#include "gemm_dmma.cuh"
+#include "panel.cuh"
+
+using namespace chol;
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+bool g_inited[64] = {false};
+
+int fail_cuda(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return int(e) > 0 ? int(e) : 1;
+}
+int fail_arg(int idx, const char* fn, const char* what) {
+    g_err = std::string(fn) + ": bad argument " + std::to_string(idx) + " (" + what + ")";
+    return -idx;
+}
+#define CHECK_LAUNCH(where)                                      \
+    do {                                                         \
+        cudaError_t e__ = cudaGetLastError();                    \
+        if (e__ != cudaSuccess) return fail_cuda(e__, where);    \
+    } while (0)
+
+int ensure_init() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice (no CUDA device: this library has no CPU fallback)");
+    if (dev < 0 || dev >= 64) return fail_arg(1, "chol_init", "device index");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_inited[dev]) return 0;
+    e = cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GEMM_SMEM_BYTES));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(gemm_nt_dmma_kernel)");
+    e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DIAG_SMEM_BYTES));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_diag_kernel)");
+    e = cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DIAG_SMEM_BYTES));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(trtri_diag_kernel)");
+    e = cudaFuncSetAttribute(potrf_batched_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(DIAG_SMEM_BYTES));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_batched_smem_kernel)");
+    e = cudaFuncSetAttribute(potrf_batched_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(batched_global_smem(BATCHED_MAX_N)));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_batched_global_kernel)");
+    g_inited[dev] = true;
+    return 0;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Enqueue the grouped update.  `fast_ok_ptrs` tells whether the caller vouches for the
+// 16-byte alignment of the tile pointers of a device task list (single tasks are checked).
+int launch_gemm(const chol_task_t* d_tasks, const chol_task_t* one, int ntasks, int m, int n, int k, int lda,
+                int ldb, int ldc, double alpha, double beta, cudaStream_t st) {
+    if (ntasks <= 0 || m <= 0 || n <= 0) return 0;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.tasks = d_tasks;
+    if (one) p.one = *one;
+    p.ntasks = ntasks;
+    p.m = m; p.n = n; p.k = k;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.alpha = alpha; p.beta = beta;
+    bool fast = (m % 2 == 0) && (n % 2 == 0) && (k % 4 == 0) && (k > 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
+                (ldc % 2 == 0);
+    if (fast && one) fast = aligned16(one->A) && aligned16(one->B) && aligned16(one->C);
+    if (fast) {
+        p.nbm = (m + BM - 1) / BM;
+        p.nbn = (n + BN - 1) / BN;
+        const long long grid = (long long)ntasks * p.nbm * p.nbn;
+        if (grid > 0x7fffffffLL) return fail_arg(2, "chol_gemm_tasks", "too many CTA tiles");
+        gemm_nt_dmma_kernel<<<dim3((unsigned)grid), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+        CHECK_LAUNCH("gemm_nt_dmma_kernel");
+    } else {
+        dim3 blk(32, 8);
+        for (int t0 = 0; t0 < ntasks; t0 += 32768) {
+            GemmParams q = p;
+            const int cnt = (ntasks - t0 < 32768) ? ntasks - t0 : 32768;
+            if (d_tasks) q.tasks = d_tasks + t0;
+            dim3 grd((m + 31) / 32, (n + 7) / 8, cnt);
+            gemm_nt_generic_kernel<<<grd, blk, 0, st>>>(q);
+            CHECK_LAUNCH("gemm_nt_generic_kernel");
+        }
+    }
+    return 0;
+}
+
+__global__ void build_trsm_tasks_kernel(double* const* tiles, int ntiles, int lda, int col_off, const double* Lrow,
+                                        const double* Winv, chol_task_t* upd, chol_task_t* mul) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntiles) return;
+    double* tile = tiles[i];
+    double* cblk = tile + size_t(col_off) * lda;
+    upd[i].C = cblk; upd[i].A = tile; upd[i].B = Lrow; upd[i].flags = 0;
+    mul[i].C = cblk; mul[i].A = cblk; mul[i].B = Winv; mul[i].flags = 0;
+}
+
+// X * L^T = A  for every tile, block column by block column (block size NBD):
+//   X_j = (A_j - sum_{l<j} X_l * L_jl^T) * inv(L_jj)^T
+int trsm_sweep(int b, const double* L, int ldl, const double* Winv, double* const* d_tiles, double* single,
+               int ntiles, int lda, chol_task_t* scratch, cudaStream_t st) {
+    const int nblk = (b + NBD - 1) / NBD;
+    for (int j = 0; j < nblk; ++j) {
+        const int o = j * NBD;
+        const int nbv = (b - o < NBD) ? b - o : NBD;
+        const double* Wj = Winv + size_t(j) * NBD * NBD;
+        if (single) {
+            chol_task_t t;
+            if (j > 0) {
+                t.C = single + size_t(o) * lda; t.A = single; t.B = L + o; t.flags = 0;
+                int rc = launch_gemm(nullptr, &t, 1, b, nbv, o, lda, ldl, lda, -1.0, 1.0, st);
+                if (rc) return rc;
+            }
+            t.C = single + size_t(o) * lda; t.A = t.C; t.B = Wj; t.flags = 0;
+            int rc = launch_gemm(nullptr, &t, 1, b, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st);
+            if (rc) return rc;
+        } else {
+            chol_task_t* upd = scratch;
+            chol_task_t* mul = scratch + ntiles;
+            build_trsm_tasks_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(d_tiles, ntiles, lda, o, L + o, Wj, upd, mul);
+            CHECK_LAUNCH("build_trsm_tasks_kernel");
+            if (j > 0) {
+                int rc = launch_gemm(upd, nullptr, ntiles, b, nbv, o, lda, ldl, lda, -1.0, 1.0, st);
+                if (rc) return rc;
+            }
+            int rc = launch_gemm(mul, nullptr, ntiles, b, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int chol_init(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+    return ensure_init();
+}
+int chol_finalize(void) { return 0; }
+const char* chol_last_error(void) { return g_err.c_str(); }
+const char* chol_version(void) { return "chol_b200 0.1 sm_100a"; }
+
+int chol_gemm_tasks(const chol_task_t* d_tasks, int ntasks, int m, int n, int k, int lda, int ldb, int ldc,
+                    double alpha, double beta, void* stream) {
+    if (ntasks < 0) return fail_arg(2, "chol_gemm_tasks", "ntasks");
+    if (ntasks > 0 && !d_tasks) return fail_arg(1, "chol_gemm_tasks", "d_tasks");
+    if (m < 0) return fail_arg(3, "chol_gemm_tasks", "m");
+    if (n < 0) return fail_arg(4, "chol_gemm_tasks", "n");
+    if (k < 0) return fail_arg(5, "chol_gemm_tasks", "k");
+    if (lda < (m > 1 ? m : 1)) return fail_arg(6, "chol_gemm_tasks", "lda");
+    if (ldb < (n > 1 ? n : 1)) return fail_arg(7, "chol_gemm_tasks", "ldb");
+    if (ldc < (m > 1 ? m : 1)) return fail_arg(8, "chol_gemm_tasks", "ldc");
+    if (int rc = ensure_init()) return rc;
+    return launch_gemm(d_tasks, nullptr, ntasks, m, n, k, lda, ldb, ldc, alpha, beta, (cudaStream_t)stream);
+}
+
+size_t chol_potrf_tile_workspace(int b) {
+    if (b <= 0) return 0;
+    return size_t((b + NBD - 1) / NBD) * NBD * NBD * sizeof(double);
+}
+
+int chol_potrf_tile(int b, double* A, int lda, double* work, int* d_info, int info_base, void* stream) {
+    if (b < 0) return fail_arg(1, "chol_potrf_tile", "b");
+    if (b == 0) return 0;
+    if (!A) return fail_arg(2, "chol_potrf_tile", "A");
+    if (lda < b) return fail_arg(3, "chol_potrf_tile", "lda");
+    if (!work) return fail_arg(4, "chol_potrf_tile", "work");
+    if (int rc = ensure_init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = (b + NBD - 1) / NBD;
+    for (int j = 0; j < nblk; ++j) {
+        const int o = j * NBD;
+        const int nbv = (b - o < NBD) ? b - o : NBD;
+        const int rem = b - o - nbv;
+        double* Wj = work + size_t(j) * NBD * NBD;
+        double* Ajj = A + size_t(o) * lda + o;
+        potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(nbv, Ajj, lda, Wj, d_info, info_base + o);
+        CHECK_LAUNCH("potrf_diag_kernel");
+        if (rem > 0) {
+            chol_task_t t;
+            // rows below the diagonal block: X = A * inv(L_jj)^T (in place; each CTA owns its rows)
+            t.C = Ajj + nbv; t.A = t.C; t.B = Wj; t.flags = 0;
+            int rc = launch_gemm(nullptr, &t, 1, rem, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st);
+            if (rc) return rc;
+            // trailing lower triangle: A22 -= X * X^T
+            t.C = A + size_t(o + nbv) * lda + (o + nbv); t.A = Ajj + nbv; t.B = t.A; t.flags = CHOL_TASK_LOWER;
+            rc = launch_gemm(nullptr, &t, 1, rem, rem, nbv, lda, lda, lda, -1.0, 1.0, st);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+size_t chol_trsm_tile_workspace(int b) { return chol_potrf_tile_workspace(b); }
+
+int chol_trsm_tile(int b, const double* L, int ldl, double* A, int lda, double* work, void* stream) {
+    if (b < 0) return fail_arg(1, "chol_trsm_tile", "b");
+    if (b == 0) return 0;
+    if (!L) return fail_arg(2, "chol_trsm_tile", "L");
+    if (ldl < b) return fail_arg(3, "chol_trsm_tile", "ldl");
+    if (!A) return fail_arg(4, "chol_trsm_tile", "A");
+    if (lda < b) return fail_arg(5, "chol_trsm_tile", "lda");
+    if (!work) return fail_arg(6, "chol_trsm_tile", "work");
+    if (int rc = ensure_init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = (b + NBD - 1) / NBD;
+    trtri_diag_kernel<<<nblk, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(b, L, ldl, work);
+    CHECK_LAUNCH("trtri_diag_kernel");
+    return trsm_sweep(b, L, ldl, work, nullptr, A, 1, lda, nullptr, st);
+}
+
+int chol_trsm_tiles(int b, const double* L, int ldl, const double* potrf_work, double* const* d_tiles, int ntiles,
+                    int lda, void* d_task_scratch, void* stream) {
+    if (b < 0) return fail_arg(1, "chol_trsm_tiles", "b");
+    if (ntiles < 0) return fail_arg(6, "chol_trsm_tiles", "ntiles");
+    if (b == 0 || ntiles == 0) return 0;
+    if (!L) return fail_arg(2, "chol_trsm_tiles", "L");
+    if (ldl < b) return fail_arg(3, "chol_trsm_tiles", "ldl");
+    if (!potrf_work) return fail_arg(4, "chol_trsm_tiles", "potrf_work");
+    if (!d_tiles) return fail_arg(5, "chol_trsm_tiles", "d_tiles");
+    if (lda < b) return fail_arg(7, "chol_trsm_tiles", "lda");
+    if (!d_task_scratch) return fail_arg(8, "chol_trsm_tiles", "d_task_scratch");
+    if (int rc = ensure_init()) return rc;
+    return trsm_sweep(b, L, ldl, potrf_work, d_tiles, nullptr, ntiles, lda, (chol_task_t*)d_task_scratch,
+                      (cudaStream_t)stream);
+}
+
+int chol_syrk_tile(int b, const double* A, int lda, double* C, int ldc, void* stream) {
+    if (b < 0) return fail_arg(1, "chol_syrk_tile", "b");
+    if (b == 0) return 0;
+    if (!A) return fail_arg(2, "chol_syrk_tile", "A");
+    if (lda < b) return fail_arg(3, "chol_syrk_tile", "lda");
+    if (!C) return fail_arg(4, "chol_syrk_tile", "C");
+    if (ldc < b) return fail_arg(5, "chol_syrk_tile", "ldc");
+    if (int rc = ensure_init()) return rc;
+    chol_task_t t;
+    t.C = C; t.A = A; t.B = A; t.flags = CHOL_TASK_LOWER;
+    return launch_gemm(nullptr, &t, 1, b, b, b, lda, lda, ldc, -1.0, 1.0, (cudaStream_t)stream);
+}
+
+int chol_gemm_tile(int b, const double* Ai, int ldai, const double* Aj, int ldaj, double* C, int ldc, void* stream) {
+    if (b < 0) return fail_arg(1, "chol_gemm_tile", "b");
+    if (b == 0) return 0;
+    if (!Ai) return fail_arg(2, "chol_gemm_tile", "Ai");
+    if (ldai < b) return fail_arg(3, "chol_gemm_tile", "ldai");
+    if (!Aj) return fail_arg(4, "chol_gemm_tile", "Aj");
+    if (ldaj < b) return fail_arg(5, "chol_gemm_tile", "ldaj");
+    if (!C) return fail_arg(6, "chol_gemm_tile", "C");
+    if (ldc < b) return fail_arg(7, "chol_gemm_tile", "ldc");
+    if (int rc = ensure_init()) return rc;
+    chol_task_t t;
+    t.C = C; t.A = Ai; t.B = Aj; t.flags = 0;
+    return launch_gemm(nullptr, &t, 1, b, b, b, ldai, ldaj, ldc, -1.0, 1.0, (cudaStream_t)stream);
+}
+
+int chol_potrf_batched(int n, int batch, double* A, int lda, long long stride, int* d_info, void* stream) {
+    if (n < 0) return fail_arg(1, "chol_potrf_batched", "n");
+    if (batch < 0) return fail_arg(2, "chol_potrf_batched", "batch");
+    if (n == 0 || batch == 0) return 0;
+    if (!A) return fail_arg(3, "chol_potrf_batched", "A");
+    if (lda < n) return fail_arg(4, "chol_potrf_batched", "lda");
+    if (stride < (long long)lda * (n - 1) + n) return fail_arg(5, "chol_potrf_batched", "stride");
+    if (!d_info) return fail_arg(6, "chol_potrf_batched", "d_info");
+    if (int rc = ensure_init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= NBD) {
+        potrf_batched_smem_kernel<<<batch, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(n, A, lda, stride, d_info);
+        CHECK_LAUNCH("potrf_batched_smem_kernel");
+    } else {
+        if (n > BATCHED_MAX_N) return fail_arg(1, "chol_potrf_batched", "n > 880: use chol_potrf_tile");
+        potrf_batched_global_kernel<<<batch, BATCHED_GLOBAL_THREADS, batched_global_smem(n), st>>>(n, A, lda, stride,
+                                                                                                 d_info);
+        CHECK_LAUNCH("potrf_batched_global_kernel");
+    }
+    return 0;
+}
+
+int chol_plgsy_tile(double bump, int mb, int nb, double* A, int lda, long long bigM, long long row0, long long col0,
+                    long long N, unsigned long long seed, void* stream) {
+    if (mb < 0) return fail_arg(2, "chol_plgsy_tile", "mb");
+    if (nb < 0) return fail_arg(3, "chol_plgsy_tile", "nb");
+    if (mb == 0 || nb == 0) return 0;
+    if (!A) return fail_arg(4, "chol_plgsy_tile", "A");
+    if (lda < mb) return fail_arg(5, "chol_plgsy_tile", "lda");
+    if (int rc = ensure_init()) return rc;
+    const int threads = 128;
+    const int rows_per_block = threads * PLGSY_ROWS_PER_THREAD;
+    dim3 grd((mb + rows_per_block - 1) / rows_per_block, nb);
+    plgsy_tile_kernel<<<grd, threads, 0, (cudaStream_t)stream>>>(bump, mb, nb, A, lda, (unsigned long long)bigM, row0,
+                                                                col0, N, seed);
+    CHECK_LAUNCH("plgsy_tile_kernel");
+    return 0;
+}
+
+int chol_tile_sumsq(int m, int n, const double* A, int lda, int mode, double* d_out, void* stream) {
+    if (m <= 0 || n <= 0) return 0;
+    if (!A) return fail_arg(3, "chol_tile_sumsq", "A");
+    if (!d_out) return fail_arg(6, "chol_tile_sumsq", "d_out");
+    if (int rc = ensure_init()) return rc;
+    const int threads = 256;
+    tile_col_sumsq_kernel<<<(n * 32 + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(m, n, A, lda, mode,
+                                                                                                  d_out);
+    CHECK_LAUNCH("tile_col_sumsq_kernel");
+    return 0;
+}
+
+int chol_tile_abs_sums(int m, int n, const double* A, int lda, int mode, double* d_rows, double* d_cols,
+                       void* stream) {
+    if (m <= 0 || n <= 0) return 0;
+    if (!A) return fail_arg(3, "chol_tile_abs_sums", "A");
+    if (int rc = ensure_init()) return rc;
+    const int threads = 256;
+    if (d_cols) {
+        tile_abs_colsum_kernel<<<(n * 32 + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(m, n, A, lda,
+                                                                                                       mode, d_cols);
+        CHECK_LAUNCH("tile_abs_colsum_kernel");
+    }
+    if (d_rows) {
+        tile_abs_rowsum_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(m, n, A, lda, mode, d_rows);
+        CHECK_LAUNCH("tile_abs_rowsum_kernel");
+    }
+    return 0;
+}
+
+int chol_tile_tril(int n, const double* A, int lda, double* B, int ldb, void* stream) {
+    if (n <= 0) return 0;
+    if (!A) return fail_arg(2, "chol_tile_tril", "A");
+    if (!B) return fail_arg(4, "chol_tile_tril", "B");
+    if (int rc = ensure_init()) return rc;
+    dim3 grd((n + 127) / 128, n);
+    tile_tril_kernel<<<grd, 128, 0, (cudaStream_t)stream>>>(n, A, lda, B, ldb);
+    CHECK_LAUNCH("tile_tril_kernel");
+    return 0;
+}
+
+int chol_fp64_peak(int kind, int iters, double* flops_out, void* stream) {
+    if (!flops_out) return fail_arg(3, "chol_fp64_peak", "flops_out");
+    if (int rc = ensure_init()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_out, 8);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double flops = 0;
+    for (int rep = 0; rep < 2; ++rep) {  // rep 0 = warm-up
+        cudaEventRecord(e0, st);
+        if (kind == 0) {
+            peak_dfma_kernel<<<sms, 1024, 0, st>>>(iters, d_out);
+            flops = double(sms) * 1024 * 16 * 2.0 * iters;
+        } else {
+            const int warps = kind == 1 ? 8 : (kind == 2 ? 16 : 4);
+            peak_dmma_kernel<<<sms, warps * 32, 0, st>>>(iters, d_out);
+            flops = double(sms) * warps * 32 * 512.0 * iters;
+        }
+        cudaEventRecord(e1, st);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+    }
+    float ms = 0;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail_cuda(e, "chol_fp64_peak");
+    *flops_out = flops / (double(ms) * 1e-3);
+    return 0;
+}
+
+}  // extern "C"

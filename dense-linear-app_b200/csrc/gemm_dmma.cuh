@@ -1,0 +1,279 @@
+// gemm_dmma.cuh — grouped FP64 rank-K update on the sm_100a DMMA path.
+//
+//   C_t <- beta*C_t + alpha * A_t * B_t^T        for every task t of a task list
+//
+// This one kernel is the hot path of the tiled Cholesky: with alpha=-1, beta=1 it is the
+// GEMM tile op (W2:511 CHAMELEON_dgemm_Tile(NoTrans,Trans,-1,Ai,Aj,1,C)), with the LOWER
+// flag the SYRK tile op (W2:416 CHAMELEON_dsyrk_Tile(Lower,NoTrans,-1,A,1,C)), and a task
+// list holding every (i,j) of one wave of the client loop (C1:307-329) is the fused
+// per-panel trailing update.  With alpha=1, beta=0 and B = inverse of a diagonal block it
+// is the multiply step of the blocked TRSM (W2:323).
+//
+// Design (B200):
+//   * CTA tile 128x128, K sliced in slabs of 16; 8 consumer warps (2 x 4) each own a
+//     64x32 sub-tile held in registers as 32 m8n8k4 DMMA accumulators (64 doubles);
+//   * 1 producer warp stages slabs with the TMA engine: one `cp.async.bulk` (UBLKCP) per
+//     slab column (a column of a col-major tile is contiguous), completion counted on an
+//     mbarrier (full/empty ring, 6 stages = 198 KB of the 227 KB shared memory);
+//   * slab columns are placed at a pitch of 132 doubles (128 + 4): the fragment loads are
+//     LDS.128 with lane -> (k = lane&3, rows 2*(lane>>2)..+1), which that pitch makes
+//     bank-conflict free (each quarter warp covers all 8 16-byte bank groups);
+//   * one LDS.128 feeds two DMMAs (even/odd rows), so a k4 step is 6 LDS.128 : 32 DMMA;
+//   * C is read-modify-written straight from the accumulators: each lane owns 2x4
+//     patches (2 consecutive rows x 4 consecutive columns) -> 16-byte accesses, every
+//     warp-wide access covers four full 128-byte lines; the producer prefetches the C
+//     block into L2 while the main loop runs.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/chol_b200.h"
+
+namespace chol {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 6;
+constexpr int PITCH = BM + 4;                       // doubles per slab column in smem
+constexpr int SLAB_DOUBLES = BK * PITCH;            // one operand slab
+constexpr int STAGE_DOUBLES = 2 * SLAB_DOUBLES;     // A slab + B slab
+constexpr int GEMM_CONSUMER_WARPS = 8;
+constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;
+constexpr size_t GEMM_SMEM_BYTES = size_t(STAGES) * STAGE_DOUBLES * 8 + 2 * STAGES * 8 + 16;
+
+struct GemmParams {
+    const chol_task_t* tasks;   // device array, or nullptr -> `one`
+    chol_task_t one;
+    int ntasks;
+    int m, n, k;
+    int lda, ldb, ldc;
+    int nbm, nbn;               // CTA blocks per task
+    double alpha, beta;
+};
+
+// ---- PTX helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA engine 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core (SASS: DMMA.8x8x4).
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- the kernel --------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * STAGE_DOUBLES);
+    // bars[0..STAGES) = full, bars[STAGES..2*STAGES) = empty
+
+    const int nsub = p.nbm * p.nbn;
+    const int task_id = blockIdx.x / nsub;
+    const int sub = blockIdx.x - task_id * nsub;
+    const int bm = sub % p.nbm;
+    const int bn = sub / p.nbm;
+
+    chol_task_t task;
+    if (p.tasks) {
+        // 32-byte task record, two 16-byte loads
+        const int4* tp = reinterpret_cast<const int4*>(p.tasks + task_id);
+        int4 lo = __ldg(tp), hi = __ldg(tp + 1);
+        task.C = reinterpret_cast<double*>((uint64_t(uint32_t(lo.y)) << 32) | uint32_t(lo.x));
+        task.A = reinterpret_cast<const double*>((uint64_t(uint32_t(lo.w)) << 32) | uint32_t(lo.z));
+        task.B = reinterpret_cast<const double*>((uint64_t(uint32_t(hi.y)) << 32) | uint32_t(hi.x));
+        task.flags = (int64_t(hi.w) << 32) | uint32_t(hi.z);
+    } else {
+        task = p.one;
+    }
+    const bool lower = (task.flags & CHOL_TASK_LOWER) != 0;
+    if (lower && bn > bm) return;  // block strictly above the diagonal: nothing to do
+
+    const int row0 = bm * BM, col0 = bn * BN;
+    const int mv = min(BM, p.m - row0);  // valid rows / cols of this block
+    const int nv = min(BN, p.n - col0);
+    const int nk = (p.k + BK - 1) / BK;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);                              // producer's expect_tx arrive
+            mbar_init(smem_u32(&bars[STAGES + s]), GEMM_CONSUMER_WARPS);   // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == GEMM_CONSUMER_WARPS) {
+        // ===================== producer warp: TMA bulk staging =====================
+        const double* gA = task.A + row0;
+        const double* gB = task.B + col0;
+        if (p.beta != 0.0) {
+            // warm L2 with this block of C for the epilogue
+            const double* gC = task.C + size_t(col0) * p.ldc + row0;
+            for (int c = lane; c < nv; c += 32) bulk_prefetch_l2(gC + size_t(c) * p.ldc, uint32_t(mv) * 8u);
+        }
+        const bool isA = lane < BK;
+        const int col = isA ? lane : lane - BK;
+        const double* gsrc = isA ? gA : gB;
+        const int ld = isA ? p.lda : p.ldb;
+        const uint32_t bytes = uint32_t(isA ? mv : nv) * 8u;
+        for (int it = 0; it < nk; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            const uint32_t full = smem_u32(&bars[s]);
+            mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1);
+            const int k0 = it * BK;
+            const int kc = min(BK, p.k - k0);
+            if (lane == 0) mbar_expect_tx(full, uint32_t(kc) * uint32_t(mv + nv) * 8u);
+            __syncwarp();
+            if (col < kc) {
+                double* dst = smem + size_t(s) * STAGE_DOUBLES + (isA ? 0 : SLAB_DOUBLES) + col * PITCH;
+                bulk_g2s(smem_u32(dst), gsrc + size_t(k0 + col) * ld, bytes, full);
+            }
+        }
+        return;
+    }
+
+    // ========================= consumer warps: DMMA main loop ==========================
+    const int wm = warp & 1;   // 2 warps along m (64 rows each)
+    const int wn = warp >> 1;  // 4 warps along n (32 cols each)
+    const int g = lane >> 2;   // mma group id  -> rows 2g, 2g+1 of a 16-row block
+    const int t = lane & 3;    // thread in group -> k index / columns 4t..4t+3
+
+    // acc[q][r][mp][np][e]: 16x16 block (q along m, r along n), mma (mp,np), element e
+    double acc[4][2][2][2][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int mp = 0; mp < 2; ++mp)
+#pragma unroll
+                for (int np = 0; np < 2; ++np) acc[q][r][mp][np][0] = acc[q][r][mp][np][1] = 0.0;
+
+    const int a_off = t * PITCH + wm * 64 + 2 * g;                  // + q*16 + kk*PITCH
+    const int b_off = SLAB_DOUBLES + t * PITCH + wn * 32 + 2 * g;   // + r*16 + kk*PITCH
+
+    for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(smem_u32(&bars[s]), ph);
+        const double* st = smem + size_t(s) * STAGE_DOUBLES;
+        const int kc = min(BK, p.k - it * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            if (kk < kc) {
+                double2 a[4], b[2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    a[q] = *reinterpret_cast<const double2*>(st + a_off + kk * PITCH + q * 16);
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    b[r] = *reinterpret_cast<const double2*>(st + b_off + kk * PITCH + r * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        dmma884(acc[q][r][0][0][0], acc[q][r][0][0][1], a[q].x, b[r].x);
+                        dmma884(acc[q][r][0][1][0], acc[q][r][0][1][1], a[q].x, b[r].y);
+                        dmma884(acc[q][r][1][0][0], acc[q][r][1][0][1], a[q].y, b[r].x);
+                        dmma884(acc[q][r][1][1][0], acc[q][r][1][1][1], a[q].y, b[r].y);
+                    }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
+    }
+
+    // ================================ epilogue ========================================
+    const double alpha = p.alpha, beta = p.beta;
+    const bool diag_block = lower && (bm == bn);
+    double* gC = task.C + size_t(col0) * p.ldc + row0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r_loc = wm * 64 + q * 16 + 2 * g;  // first of the two rows this lane owns
+        if (r_loc >= mv) continue;                   // mv is even: the pair is in or out together
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    const int c_loc = wn * 32 + r * 16 + 4 * t + 2 * e + np;
+                    if (c_loc >= nv) continue;
+                    double* ptr = gC + size_t(c_loc) * p.ldc + r_loc;
+                    double v0 = alpha * acc[q][r][0][np][e];
+                    double v1 = alpha * acc[q][r][1][np][e];
+                    if (diag_block && r_loc < c_loc) {
+                        // pair straddles or lies above the diagonal
+                        if (r_loc + 1 == c_loc) {
+                            if (beta != 0.0) v1 += beta * ptr[1];
+                            ptr[1] = v1;
+                        }
+                        continue;
+                    }
+                    if (beta != 0.0) {
+                        const double2 old = *reinterpret_cast<const double2*>(ptr);
+                        v0 += beta * old.x;
+                        v1 += beta * old.y;
+                    }
+                    *reinterpret_cast<double2*>(ptr) = make_double2(v0, v1);
+                }
+        }
+    }
+}
+
+// ---- generic fallback for shapes the fast path cannot take (odd sizes, unaligned) ------
+// Plain CUDA, one thread per C element.  Only ever used for tiny / odd tiles (e.g. the
+// client's default B=4, C2:350) where speed is irrelevant; still GPU code, never the CPU.
+__global__ void gemm_nt_generic_kernel(const GemmParams p) {
+    const int task_id = blockIdx.z;
+    chol_task_t task = p.tasks ? p.tasks[task_id] : p.one;
+    const bool lower = (task.flags & CHOL_TASK_LOWER) != 0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= p.m || j >= p.n) return;
+    if (lower && i < j) return;
+    double s = 0.0;
+    for (int l = 0; l < p.k; ++l) s = fma(task.A[size_t(l) * p.lda + i], task.B[size_t(l) * p.ldb + j], s);
+    double* c = task.C + size_t(j) * p.ldc + i;
+    double v = p.alpha * s;
+    if (p.beta != 0.0) v += p.beta * *c;
+    *c = v;
+}
+
+}  // namespace chol

@@ -1,0 +1,146 @@
+/*
+ * chol_b200.h — C ABI of libchol_b200.so: B200 (sm_100a) tiled FP64 Cholesky.
+ *
+ * Drop-in boundary for the ONE hot path of HugoVuach/Dense-linear-app: the tile-task
+ * Cholesky (POTRF / TRSM / SYRK / GEMM on b x b column-major FP64 tiles).  Every entry
+ * point names the reference interface it replaces (paths under /root/reference):
+ *   W2  = cholesky_armonik/w_c_cons_v2/worker_construction2/src/worker_distrib.cpp
+ *   C1  = cholesky_armonik/w_c_cons_v1/client_construction/client/src/client_distrib.cpp
+ *   V6  = Cholesky_chameleon_VM/cho/docker_installation_and_bench_files/v6_test.c
+ *
+ * Conventions
+ *   - all matrix pointers are DEVICE pointers unless the name ends in _host;
+ *   - tiles are column-major, FP64, operated on in place (W2:76-79, W2:212-227);
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are
+ *     asynchronous on that stream, nothing here synchronises the device;
+ *   - return value: 0 ok, <0 = -(index of the bad argument) (LAPACK style),
+ *     >0 = CUDA runtime error code (see chol_last_error()).  Numerical failure
+ *     (matrix not positive definite) is reported through the device int `d_info`
+ *     exactly like LAPACK dpotrf's info (1-based index of the failing minor, first
+ *     failure wins, 0 = success) because the result is only known when the stream
+ *     has run;
+ *   - no function allocates user-visible memory; scratch comes from the caller and is
+ *     sized by the *_workspace() queries;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns
+ *     an error.
+ */
+#ifndef CHOL_B200_H
+#define CHOL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------- */
+
+/* CHAMELEON_Init(ncpu, ngpu) analogue (V6:41, W2:589): selects the device and sets the
+ * kernels' shared-memory attributes.  Idempotent, thread-safe. */
+int chol_init(int device);
+/* CHAMELEON_Finalize analogue (V6:93). */
+int chol_finalize(void);
+/* Text of the last error raised on this thread ("" if none). */
+const char* chol_last_error(void);
+/* Library version string, e.g. "chol_b200 0.1 sm_100a". */
+const char* chol_version(void);
+
+/* ---- grouped rank-K update: the hot kernel (K4/K5 of SURVEY 2b) ------------------ */
+
+/* One C-tile update  C <- beta*C + alpha * A * B^T  (A: m x k, B: n x k, col-major).
+ * flags bit0 (CHOL_TASK_LOWER): only the lower triangle of C is referenced and written
+ * (dsyrk uplo=Lower semantics, W2:416).  32 bytes, laid out for direct upload from a
+ * numpy/torch int64 [ntasks,4] array. */
+typedef struct chol_task {
+    double*       C;
+    const double* A;
+    const double* B;
+    int64_t       flags;
+} chol_task_t;
+#define CHOL_TASK_LOWER 1
+
+/* All tasks share m, n, k and the leading dimensions.  `d_tasks` is a DEVICE array.
+ * Replaces the per-tile SYRK/GEMM submissions of one wave of the client loop
+ * (C1:307-329, C2:541-561) by ONE persistent launch: the "fused SYRK+GEMM trailing
+ * update per panel".  Fast path (DMMA + TMA bulk staging) needs m,n even, k%4==0,
+ * even leading dimensions and 16-byte aligned tile pointers; other shapes take the
+ * generic CUDA kernel. */
+int chol_gemm_tasks(const chol_task_t* d_tasks, int ntasks, int m, int n, int k,
+                    int lda, int ldb, int ldc, double alpha, double beta, void* stream);
+
+/* ---- the four tile ops of the worker (W2:179-546) -------------------------------- */
+
+/* POTRF: A <- chol_lower(A); strict upper triangle untouched.
+ * Replaces CHAMELEON_dpotrf_Tile(ChamLower, dA) on a 1-tile descriptor (W2:238).
+ * `work` >= chol_potrf_tile_workspace(b) bytes; on return it holds the inverses of the
+ * 128x128 diagonal blocks of L (input for chol_trsm_tiles).  `info_base` is added to a
+ * failing index so a whole-matrix driver gets the global LAPACK info (V6:56). */
+size_t chol_potrf_tile_workspace(int b);
+int chol_potrf_tile(int b, double* A, int lda, double* work, int* d_info, int info_base,
+                    void* stream);
+
+/* TRSM: A <- A * L^{-T}   (Right, Lower, Trans, NonUnit, alpha=1).
+ * Replaces CHAMELEON_dtrsm_Tile(ChamRight,ChamLower,ChamTrans,ChamNonUnit,1.0,dL,dA)
+ * (W2:323).  Stateless form: inverts the diagonal blocks of L into `work`
+ * (>= chol_trsm_tile_workspace(b) bytes) first. */
+size_t chol_trsm_tile_workspace(int b);
+int chol_trsm_tile(int b, const double* L, int ldl, double* A, int lda, double* work,
+                   void* stream);
+
+/* Panel form: the same solve applied to `ntiles` tiles (device array of tile pointers)
+ * in one launch sequence, re-using the diagonal-block inverses left in `potrf_work` by
+ * chol_potrf_tile.  `d_task_scratch` >= ntiles*sizeof(chol_task_t)*2 bytes of device
+ * scratch.  Replaces the TRSM loop of one wave (C1:295-303). */
+int chol_trsm_tiles(int b, const double* L, int ldl, const double* potrf_work,
+                    double* const* d_tiles, int ntiles, int lda, void* d_task_scratch,
+                    void* stream);
+
+/* SYRK: C <- C - A*A^T, lower triangle only.
+ * Replaces CHAMELEON_dsyrk_Tile(ChamLower,ChamNoTrans,-1.0,dA,1.0,dC) (W2:416). */
+int chol_syrk_tile(int b, const double* A, int lda, double* C, int ldc, void* stream);
+
+/* GEMM: C <- C - Ai*Aj^T.
+ * Replaces CHAMELEON_dgemm_Tile(ChamNoTrans,ChamTrans,-1.0,dAi,dAj,1.0,dC) (W2:511). */
+int chol_gemm_tile(int b, const double* Ai, int ldai, const double* Aj, int ldaj,
+                   double* C, int ldc, void* stream);
+
+/* ---- batched small Cholesky (the ArmoniK many-task workload, C1:139-141) ---------- */
+
+/* `batch` independent n x n lower Cholesky factorizations, matrix i at A + i*stride
+ * (doubles).  d_info[i] = LAPACK info of matrix i. */
+int chol_potrf_batched(int n, int batch, double* A, int lda, long long stride,
+                       int* d_info, void* stream);
+
+/* ---- generators and checks (V6:46, V6:51, V6:72-86; off the timed path) ----------- */
+
+/* dplgsy-like tile generator (V6:46 CHAMELEON_dplgsy_Tile(bump, ChamLower, desc, seed)):
+ * fills the mb x nb tile whose top-left element is (row0, col0) of the symmetric N x N
+ * matrix; element (i,j), i>=j, is 0.5 - LCG^(i + j*bigM)(seed) * 2^-64; diagonal += bump.
+ * Elements beyond the matrix edge (row/col >= N) are set to the identity so ragged
+ * edge tiles stay positive definite. */
+int chol_plgsy_tile(double bump, int mb, int nb, double* A, int lda, long long bigM,
+                    long long row0, long long col0, long long N, unsigned long long seed,
+                    void* stream);
+
+/* sum of squares of a tile -> d_out[0] (mode 0: all m x n entries; mode 1: lower triangle
+ * counted as a symmetric matrix, i.e. strict lower twice + diagonal once). */
+int chol_tile_sumsq(int m, int n, const double* A, int lda, int mode, double* d_out,
+                    void* stream);
+/* per-row and per-column sums of |a_ij| of a tile (mode as above: mode 1 reads only the
+ * lower triangle).  d_rows[m], d_cols[n].  Building block of dlange(inf) (V6:72,84). */
+int chol_tile_abs_sums(int m, int n, const double* A, int lda, int mode, double* d_rows,
+                       double* d_cols, void* stream);
+/* B <- lower triangle of A, strict upper zeroed (dlacpy(ChamLower), V6:77). */
+int chol_tile_tril(int n, const double* A, int lda, double* B, int ldb, void* stream);
+
+/* ---- microbenchmarks for the roofline denominators -------------------------------- */
+
+/* kind 0: DFMA chains, 1: DMMA m8n8k4 chains.  Runs `iters` inner iterations on every
+ * SM, returns achieved FLOP/s in *flops_out (timed with CUDA events on `stream`). */
+int chol_fp64_peak(int kind, int iters, double* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHOL_B200_H */
