@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(1024, 1) peak_dfma_kernel(int iters, double* o
     if (s == 12345.678) out[0] = s;
 }
 // kind 1..3: 32 independent m8n8k4 DMMA accumulators per warp (same ILP as the GEMM).
-__global__ void peak_dmma_kernel(int iters, double* out) {
+__global__ void __launch_bounds__(256, 1) peak_dmma_kernel(int iters, double* out) {
     double acc[32][2];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i][0] = acc[i][1] = 0.0;

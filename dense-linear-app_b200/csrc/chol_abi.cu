@@ -366,10 +366,12 @@ int chol_fp64_peak(int kind, int iters, double* flops_out, void* stream) {
             peak_dfma_kernel<<<sms, 1024, 0, st>>>(iters, d_out);
             flops = double(sms) * 1024 * 16 * 2.0 * iters;
         } else {
-            const int warps = kind == 1 ? 8 : (kind == 2 ? 16 : 4);
+            const int warps = kind == 1 ? 8 : 4;
             peak_dmma_kernel<<<sms, warps * 32, 0, st>>>(iters, d_out);
             flops = double(sms) * warps * 32 * 512.0 * iters;
         }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) break;
         cudaEventRecord(e1, st);
         e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) break;

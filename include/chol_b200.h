@@ -136,7 +136,7 @@ int chol_tile_tril(int n, const double* A, int lda, double* B, int ldb, void* st
 
 /* ---- microbenchmarks for the roofline denominators -------------------------------- */
 
-/* kind 0: DFMA chains, 1: DMMA m8n8k4 chains.  Runs `iters` inner iterations on every
+/* kind 0: DFMA chains, 1: DMMA m8n8k4 chains on 8 warps per SM, 2: same on 4 warps.  Runs `iters` inner iterations on every
  * SM, returns achieved FLOP/s in *flops_out (timed with CUDA events on `stream`). */
 int chol_fp64_peak(int kind, int iters, double* flops_out, void* stream);
 
