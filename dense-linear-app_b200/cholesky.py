@@ -1,0 +1,385 @@
+"""Right-looking tiled Cholesky on one or several B200s: the host side.
+
+Replaces ``CHAMELEON_dpotrf_Tile(ChamLower, descA)`` (v6_test.c:56) and the client's wave loop
+(client_distrib.cpp v1:278-333 / v2:506-565): for each k, POTRF(k,k); TRSM(i,k) for i>k; then
+SYRK(i,i) / GEMM(i,j) for i>=j>k.  Python builds that DAG once as a *plan* (per-step device
+task lists of tile pointers) and then only enqueues kernels of ``libchol_b200.so`` through
+ctypes; torch provides the buffers, streams, events and the NCCL broadcasts.
+
+Schedule (per rank; one rank per GPU, tiles 2D block-cyclic, see grid.py):
+  * panel stream (high priority): POTRF of the diagonal tile on its owner, broadcast of L_kk and
+    the inverted diagonal blocks down the owner's process column, TRSM of the panel tiles on
+    their owners (one grouped launch sequence), broadcast of the factored panel to all ranks;
+  * update stream: the fused SYRK+GEMM trailing update of step k as ONE grouped launch over
+    every local tile (i,j), i>=j>k — split in two so that column k+1 is finished first
+    (part a) and the panel stream can factor panel k+1 while the rest (part b) still runs:
+    lookahead of depth 1.
+Nothing synchronises with the host between steps; LAPACK ``info`` is a device int read at the end.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .grid import panel_slots
+from .tiles import TileMatrix
+
+
+class TiledCholesky:
+    """Plan + executor for the in-place factorization of a TileMatrix (lower, A = L L^T)."""
+
+    def __init__(self, A: TileMatrix, group=None, lookahead: bool = True):
+        self.A = A
+        self.nt, self.b = A.nt, A.b
+        self.grid, self.rank, self.lay = A.grid, A.rank, A.layout
+        self.dev = A.device
+        self.cuda = self.dev.type == "cuda"
+        self.world = self.grid.size
+        self.group = group
+        self.lookahead = lookahead
+        if self.world > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError("a P x Q grid with more than one rank needs torch.distributed initialised")
+            if dist.get_world_size(group) != self.world:
+                raise RuntimeError(f"process group has {dist.get_world_size(group)} ranks, grid needs {self.world}")
+        b, nt = self.b, self.nt
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.tile_bytes = b * b * 8
+        # workspace: inverted 128x128 diagonal blocks of L_kk (chol_potrf_tile -> chol_trsm_tiles)
+        self.work = torch.empty(max(self._potrf_workspace(b) // 8, 1), **f64)
+        self.d_info = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        # receive buffers (only with more than one rank): panel column k, two slots for lookahead
+        self.panel = None
+        self.diag = None
+        if self.world > 1:
+            self.panel = torch.empty((2, max(nt - 1, 1), b, b), **f64)
+            self.diag = torch.empty((b, b), **f64)
+        self._col_groups = None
+        self._build_plan()
+        if self.cuda:
+            self.s_update = torch.cuda.Stream(self.dev)
+            self.s_panel = torch.cuda.Stream(self.dev, priority=-1)
+        else:
+            self.s_update = self.s_panel = None
+
+    # ---- kernel entry points (the C ABI); tests override these on CPU tensors ----------------
+    def _potrf_workspace(self, b: int) -> int:
+        return _lib.load().chol_potrf_tile_workspace(b)
+
+    def _k_potrf(self, a_ptr: int, info_base: int, st: int) -> None:
+        _lib.call("chol_potrf_tile", self.b, a_ptr, self.b, self.work.data_ptr(), self.d_info.data_ptr(), info_base, st)
+
+    def _k_trsm_panel(self, l_ptr: int, tiles_ptr: int, ntiles: int, st: int) -> None:
+        _lib.call("chol_trsm_tiles", self.b, l_ptr, self.b, self.work.data_ptr(), tiles_ptr, ntiles, self.b,
+                  self.trsm_scratch.data_ptr(), st)
+
+    def _k_update(self, tasks_ptr: int, ntasks: int, st: int) -> None:
+        b = self.b
+        _lib.call("chol_gemm_tasks", tasks_ptr, ntasks, b, b, b, b, b, b, -1.0, 1.0, st)
+
+    def _k_tril(self, src_ptr: int, dst_ptr: int, st: int) -> None:
+        _lib.call("chol_tile_tril", self.b, src_ptr, self.b, dst_ptr, self.b, st)
+
+    def _bcast(self, t: torch.Tensor, src: int, group) -> None:
+        import torch.distributed as dist
+        dist.broadcast(t, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+
+    # ---- plan ----------------------------------------------------------------------------------
+    def _panel_ptrs(self, k: int, base_local: int) -> np.ndarray:
+        """Address, on this rank, of every tile (i, k): local storage if owned, else the receive
+        buffer slot of step k.  Entries for i <= k are 0."""
+        nt, tb = self.nt, self.tile_bytes
+        ptr = np.zeros(nt, dtype=np.int64)
+        if self.world == 1:
+            rows = np.arange(k + 1, nt)
+            ptr[rows] = base_local + (self.lay.col_start[k] + rows - k) * tb
+            return ptr
+        slot, _ = panel_slots(nt, self.grid.P, k)
+        pbase = self.panel.data_ptr() + (k % 2) * self.panel.stride(0) * 8
+        mine_col = (k % self.grid.Q) == self.lay.q
+        for i in range(k + 1, nt):
+            if mine_col and i % self.grid.P == self.lay.p:
+                ptr[i] = base_local + self.lay.index(i, k) * tb
+            else:
+                ptr[i] = pbase + slot[i] * tb
+        return ptr
+
+    def _update_tasks(self, k: int, c_base: int, a_ptr: np.ndarray) -> tuple[np.ndarray, int]:
+        """Task records (C, A, B, flags) of the trailing update of step k for the local tiles
+        (i,j), i>=j>k: C_ij -= A_ik A_jk^T, lower only when i == j (client loop v1:307-329).
+        Column k+1 first (part a); returns (tasks[n,4], n_part_a)."""
+        lay, tb, P = self.lay, self.tile_bytes, self.grid.P
+        cols = [j for j in lay.cols if j > k]
+        parts_a, parts_b = [], []
+        for j in cols:
+            rows = np.asarray(lay.rows_in_col(j, j - 1), dtype=np.int64)  # owned i >= j
+            if rows.size == 0:
+                continue
+            cidx = lay.col_start[j] + (rows - lay.col_first_row[j]) // P
+            rec = np.empty((rows.size, 4), dtype=np.int64)
+            rec[:, 0] = c_base + cidx * tb
+            rec[:, 1] = a_ptr[rows]
+            rec[:, 2] = a_ptr[j]
+            rec[:, 3] = (rows == j).astype(np.int64)
+            (parts_a if j == k + 1 else parts_b).append((rows, rec))
+        na = sum(r.shape[0] for _, r in parts_a)
+        if parts_b:
+            rows_b = np.concatenate([r for r, _ in parts_b])
+            rec_b = np.concatenate([r for _, r in parts_b])
+            # row-major over (i, j): consecutive tasks share the A operand (tile (i,k)) in L2
+            rec_b = rec_b[np.argsort(rows_b, kind="stable")]
+            recs = [r for _, r in parts_a] + [rec_b]
+        else:
+            recs = [r for _, r in parts_a]
+        if not recs:
+            return np.zeros((0, 4), dtype=np.int64), 0
+        return np.concatenate(recs), na
+
+    def _build_plan(self) -> None:
+        nt, tb = self.nt, self.tile_bytes
+        base = self.A.buf.data_ptr()
+        all_tasks, self.step_tasks = [], []   # step_tasks[k] = (offset, n_a, n_total)
+        trsm_ptrs, self.step_trsm = [], []    # step_trsm[k] = (offset, count) of owned panel tiles
+        off = toff = 0
+        self.a_ptrs = []
+        for k in range(nt):
+            a_ptr = self._panel_ptrs(k, base)
+            self.a_ptrs.append(a_ptr)
+            rec, na = self._update_tasks(k, base, a_ptr)
+            all_tasks.append(rec)
+            self.step_tasks.append((off, na, rec.shape[0]))
+            off += rec.shape[0]
+            if (k % self.grid.Q) == self.lay.q:
+                rows = np.asarray(self.lay.rows_in_col(k, k), dtype=np.int64)
+            else:
+                rows = np.zeros(0, dtype=np.int64)
+            trsm_ptrs.append(a_ptr[rows])
+            self.step_trsm.append((toff, rows.size))
+            toff += rows.size
+        tasks = np.concatenate(all_tasks) if off else np.zeros((1, 4), dtype=np.int64)
+        tptr = np.concatenate(trsm_ptrs) if toff else np.zeros(1, dtype=np.int64)
+        self.tasks_host = tasks
+        self.d_tasks = torch.from_numpy(tasks).to(self.dev)
+        self.d_trsm_ptrs = torch.from_numpy(tptr).to(self.dev)
+        max_panel = max((c for _, c in self.step_trsm), default=0)
+        self.trsm_scratch = torch.empty(max(max_panel, 1) * 8, dtype=torch.int64, device=self.dev)
+        self.n_update_tasks = off
+
+    def _column_group(self, q: int):
+        """Process group of the P ranks of grid column q (for the L_kk broadcast)."""
+        if self.grid.P == 1:
+            return None
+        if self._col_groups is None:
+            import torch.distributed as dist
+            base_ranks = list(range(self.world)) if self.group is None else dist.get_process_group_ranks(self.group)
+            self._col_groups = []
+            for qq in range(self.grid.Q):  # every rank creates every group, in the same order
+                members = [base_ranks[self.grid.rank_of(p, qq)] for p in range(self.grid.P)]
+                self._col_groups.append(dist.new_group(members))
+        return self._col_groups[q]
+
+    # ---- execution -------------------------------------------------------------------------------
+    def _stream_ptr(self, s) -> int:
+        return s.cuda_stream if s is not None else 0
+
+    def _panel_step(self, k: int, factor: bool = True) -> None:
+        """Everything of step k that happens before the trailing update: POTRF, TRSM, broadcasts.
+        Runs on the panel stream.  With factor=False only the broadcasts run (residual mode)."""
+        g, lay, nt = self.grid, self.lay, self.nt
+        st = self._stream_ptr(self.s_panel)
+        kq, kp = k % g.Q, k % g.P
+        in_col = kq == lay.q
+        is_diag = in_col and kp == lay.p
+        if factor:
+            if is_diag:
+                self._k_potrf(self.A.tile_ptr(k, k), k * self.b, st)
+            l_ptr = self.A.tile_ptr(k, k) if is_diag else 0
+            if g.P > 1 and in_col and k + 1 < nt:
+                cg = self._column_group(kq)
+                ltile = self.A.tile(k, k) if is_diag else self.diag
+                self._bcast(ltile, kp, cg)
+                self._bcast(self.work, kp, cg)
+                l_ptr = ltile.data_ptr()
+            toff, cnt = self.step_trsm[k]
+            if cnt:
+                self._k_trsm_panel(l_ptr, self.d_trsm_ptrs.data_ptr() + toff * 8, cnt, st)
+        if self.world > 1 and k + 1 < nt:
+            _, groups = panel_slots(nt, g.P, k)
+            for p, first, cnt in groups:
+                if cnt == 0:
+                    continue
+                root = g.rank_of(p, kq)
+                if root == self.rank:
+                    s0 = lay.index(lay.rows_in_col(k, k)[0], k)
+                    buf = self.A.buf[s0:s0 + cnt]
+                else:
+                    buf = self.panel[k % 2, first:first + cnt]
+                self._bcast(buf, root, self.group)
+
+    def _run(self, update_tasks_ptr: int, factor: bool, pre_update=None) -> None:
+        nt = self.nt
+        cuda = self.cuda
+        if cuda:
+            cur = torch.cuda.current_stream(self.dev)
+            self.s_update.wait_stream(cur)
+            self.s_panel.wait_stream(cur)
+        ev_col = None      # column k ready for its panel step
+        ev_upd = [None, None]  # update k finished reading panel slot k%2
+        for k in range(nt):
+            # ---- panel k
+            if cuda:
+                with torch.cuda.stream(self.s_panel):
+                    if ev_col is not None:
+                        self.s_panel.wait_event(ev_col)
+                    if ev_upd[k % 2] is not None:
+                        self.s_panel.wait_event(ev_upd[k % 2])
+                    self._panel_step(k, factor)
+                    ev_panel = torch.cuda.Event()
+                    ev_panel.record(self.s_panel)
+                self.s_update.wait_event(ev_panel)
+            else:
+                self._panel_step(k, factor)
+            # ---- trailing update k
+            st = self._stream_ptr(self.s_update)
+            if pre_update is not None:
+                pre_update(k, st)
+            off, na, ntot = self.step_tasks[k]
+            split = na if (self.lookahead and 0 < na < ntot) else 0
+            base = update_tasks_ptr + off * 32
+            if not cuda:
+                if ntot:
+                    self._k_update(base, ntot, st)
+                continue
+            with torch.cuda.stream(self.s_update):
+                if split:
+                    # part a: column k+1, so its panel step can start while part b runs
+                    self._k_update(base, split, st)
+                    ev_col = torch.cuda.Event()
+                    ev_col.record(self.s_update)
+                    self._k_update(base + split * 32, ntot - split, st)
+                    ev_upd[k % 2] = torch.cuda.Event()
+                    ev_upd[k % 2].record(self.s_update)
+                else:
+                    if ntot:
+                        self._k_update(base, ntot, st)
+                    ev_upd[k % 2] = torch.cuda.Event()
+                    ev_upd[k % 2].record(self.s_update)
+                    # a rank that owns nothing in column k+1 only receives panel k+1: it may
+                    # join that broadcast as soon as the receive slot is free (ev_upd of k-1)
+                    ev_col = None if (self.lookahead and na == 0) else ev_upd[k % 2]
+        if cuda:
+            cur.wait_stream(self.s_update)
+            cur.wait_stream(self.s_panel)
+
+    def factor(self) -> None:
+        """Enqueue the whole factorization (asynchronous on CUDA).  A <- L (lower tiles)."""
+        self.d_info.zero_()
+        self._run(self.d_tasks.data_ptr(), factor=True)
+
+    def info(self) -> int:
+        """LAPACK info of the last factor(): 0, or the 1-based global index of the first
+        non-positive pivot (v6_test.c:56,95).  Synchronises; with several ranks the smallest
+        non-zero value over the ranks is returned on every rank."""
+        v = int(self.d_info.item())
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([v if v > 0 else 2 ** 31 - 1], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            v = int(t.item())
+            v = 0 if v == 2 ** 31 - 1 else v
+        return v
+
+    # ---- residual: R = A0 - L L^T with the same schedule ---------------------------------------
+    def residual(self, A0: TileMatrix) -> dict:
+        """Overwrite A0 (same geometry as A, holding the original matrix) with the lower tiles of
+        R = A0 - L L^T and return {"fro": ||R||_F/||A0||_F, "inf": ||R||_inf/||A0||_inf}: what
+        v6_test.c:72-86 means to print (its dlauum forms L^T L instead).  Runs the
+        factorization's own broadcast/update schedule with C pointing into A0."""
+        assert A0.desc == self.A.desc and A0.rank == self.rank
+        b, nt, tb, lay, g = self.b, self.nt, self.tile_bytes, self.lay, self.grid
+        na_f, na_i = _norms(A0, self)
+        # tril(L_kk) for every k this rank needs: broadcast from the diag owner to everyone
+        tk = torch.empty((2, b, b), dtype=torch.float64, device=self.dev)
+        shift = A0.buf.data_ptr() - self.A.buf.data_ptr()
+        tasks = self.tasks_host.copy()
+        tasks[:, 0] += shift
+        d_tasks = torch.from_numpy(tasks).to(self.dev) if self.n_update_tasks else self.d_tasks
+        col_tasks = {}
+        for k in range(nt):
+            if (k % g.Q) != lay.q:
+                continue
+            rows = np.asarray(lay.rows_in_col(k, k - 1), dtype=np.int64)
+            if rows.size == 0:
+                continue
+            rec = np.empty((rows.size, 4), dtype=np.int64)
+            rec[:, 0] = [A0.tile_ptr(int(i), k) for i in rows]
+            rec[:, 1] = [tk[k % 2].data_ptr() if i == k else self.A.tile_ptr(int(i), k) for i in rows]
+            rec[:, 2] = tk[k % 2].data_ptr()
+            rec[:, 3] = (rows == k).astype(np.int64)
+            col_tasks[k] = torch.from_numpy(rec).to(self.dev)
+
+        def pre_update(k: int, st: int) -> None:
+            # T_k = tril(L_kk) on its owner, sent down the process column, then column k of R
+            kq, kp = k % g.Q, k % g.P
+            if kq != lay.q:
+                return
+            ctx = torch.cuda.stream(self.s_update) if self.cuda else _Null()
+            with ctx:
+                if kp == lay.p:
+                    self._k_tril(self.A.tile_ptr(k, k), tk[k % 2].data_ptr(), st)
+                if g.P > 1:
+                    self._bcast(tk[k % 2], kp, self._column_group(kq))
+                if k in col_tasks:
+                    self._k_update(col_tasks[k].data_ptr(), col_tasks[k].shape[0], st)
+
+        self._run(d_tasks.data_ptr(), factor=False, pre_update=pre_update)
+        nr_f, nr_i = _norms(A0, self)
+        return {"fro": nr_f / na_f, "inf": nr_i / na_i, "norm_fro": na_f, "norm_inf": na_i}
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def _norms(M: TileMatrix, ch: TiledCholesky) -> tuple[float, float]:
+    """Frobenius and infinity norm of the symmetric matrix whose lower tiles are M (the strict
+    upper triangle of diagonal tiles is ignored).  Plain torch reductions on the tile buffer:
+    off the timed path (v6_test.c:72,84 dlange)."""
+    b, nt = M.b, M.nt
+    rows = torch.zeros(nt * b, dtype=torch.float64, device=M.device)
+    ssq = torch.zeros((), dtype=torch.float64, device=M.device)
+    for i, j in M.layout.tiles():
+        t = M.tile(i, j)  # t[c, r] = A(r, c)
+        if i == j:
+            low = torch.triu(t)          # torch-upper of the transposed view == lower triangle of the tile
+            strict = torch.triu(t, 1)
+            ssq += (low * low).sum() + (strict * strict).sum()
+            a = low.abs()
+            rows[i * b:(i + 1) * b] += a.sum(0) + strict.abs().sum(1)
+        else:
+            ssq += 2.0 * (t * t).sum()
+            a = t.abs()
+            rows[i * b:(i + 1) * b] += a.sum(0)   # sum over columns c -> per row r of block i
+            rows[j * b:(j + 1) * b] += a.sum(1)   # mirrored tile (j,i): per column c
+    if ch.world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(rows, group=ch.group)
+        dist.all_reduce(ssq, group=ch.group)
+    return float(ssq.sqrt().item()), float(rows.max().item())
+
+
+def potrf_tile_desc(uplo: str, A: TileMatrix, group=None, lookahead: bool = True) -> int:
+    """int CHAMELEON_dpotrf_Tile(cham_uplo_t uplo, CHAM_desc_t *A) (v6_test.c:56): in-place lower
+    Cholesky of the tiled SPD matrix; returns LAPACK info.  Only uplo = 'L' (ChamLower) — the one
+    the reference calls."""
+    if uplo not in ("L", "l"):
+        raise ValueError("only uplo='L' (ChamLower) is supported")
+    ch = TiledCholesky(A, group=group, lookahead=lookahead)
+    ch.factor()
+    return ch.info()
