@@ -16,6 +16,7 @@ SIGNATURES = {
     "chol_finalize": (c_int, []),
     "chol_last_error": (C.c_char_p, []),
     "chol_version": (C.c_char_p, []),
+    "chol_launch_count": (c_ull, []),
     "chol_gemm_tasks": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_void_p]),
     "chol_potrf_tile_workspace": (c_size_t, [c_int]),
     "chol_potrf_tile": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),

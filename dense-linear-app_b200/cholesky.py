@@ -57,6 +57,7 @@ class TiledCholesky:
             self.panel = torch.empty((2, max(nt - 1, 1), b, b), **f64)
             self.diag = torch.empty((b, b), **f64)
         self._col_groups = None
+        self.update_events = None   # set to [] to time every trailing-update launch (bench.py roofline)
         self._build_plan()
         if self.cuda:
             self.s_update = torch.cuda.Stream(self.dev)
@@ -77,7 +78,17 @@ class TiledCholesky:
 
     def _k_update(self, tasks_ptr: int, ntasks: int, st: int) -> None:
         b = self.b
+        if self.update_events is None:
+            _lib.call("chol_gemm_tasks", tasks_ptr, ntasks, b, b, b, b, b, b, -1.0, 1.0, st)
+            return
+        # CUDA events on the launching stream around this one launch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.s_update)
         _lib.call("chol_gemm_tasks", tasks_ptr, ntasks, b, b, b, b, b, b, -1.0, 1.0, st)
+        e1.record(self.s_update)
+        first = (tasks_ptr - self.d_tasks.data_ptr()) // 32
+        nsyrk = int(self.tasks_host[first:first + ntasks, 3].sum()) if 0 <= first < len(self.tasks_host) else 0
+        self.update_events.append((e0, e1, (2 * ntasks - nsyrk) * float(b) ** 3))
 
     def _k_tril(self, src_ptr: int, dst_ptr: int, st: int) -> None:
         _lib.call("chol_tile_tril", self.b, src_ptr, self.b, dst_ptr, self.b, st)
@@ -218,7 +229,7 @@ class TiledCholesky:
                     buf = self.panel[k % 2, first:first + cnt]
                 self._bcast(buf, root, self.group)
 
-    def _run(self, update_tasks_ptr: int, factor: bool, pre_update=None) -> None:
+    def _run(self, update_tasks_ptr: int, factor: bool, pre_update=None, post_panel=None) -> None:
         nt = self.nt
         cuda = self.cuda
         if cuda:
@@ -239,6 +250,8 @@ class TiledCholesky:
                     ev_panel = torch.cuda.Event()
                     ev_panel.record(self.s_panel)
                 self.s_update.wait_event(ev_panel)
+                if post_panel is not None:
+                    post_panel(k, ev_panel)
             else:
                 self._panel_step(k, factor)
             # ---- trailing update k
@@ -277,6 +290,36 @@ class TiledCholesky:
         """Enqueue the whole factorization (asynchronous on CUDA).  A <- L (lower tiles)."""
         self.d_info.zero_()
         self._run(self.d_tasks.data_ptr(), factor=True)
+
+    def factor_from_host(self, host_in: torch.Tensor, host_out: torch.Tensor | None = None) -> None:
+        """End-to-end form for callers whose tiles live in HOST memory (the tile-worker situation,
+        worker_distrib.cpp:186,261): `host_in` is a pinned CPU tensor shaped like ``A.buf`` holding
+        this rank's tiles; they are copied to the device, factored, and the factor is copied back
+        into `host_out` (default: `host_in`).  Panel column k is final once its panel step is done,
+        so its device-to-host copy runs on a copy stream underneath the remaining updates.
+        Asynchronous; synchronise the current stream before reading `host_out`."""
+        if not self.cuda:
+            raise RuntimeError("factor_from_host needs a CUDA device")
+        host_out = host_in if host_out is None else host_out
+        assert host_in.shape == self.A.buf.shape and host_in.is_pinned() and host_out.is_pinned()
+        cur = torch.cuda.current_stream(self.dev)
+        if getattr(self, "s_copy", None) is None:
+            self.s_copy = torch.cuda.Stream(self.dev)
+        self.A.buf.copy_(host_in, non_blocking=True)
+        self.d_info.zero_()
+        lay, nt = self.lay, self.nt
+        bounds = {j: (lay.col_start[j], lay.col_start[lay.cols[n + 1]] if n + 1 < len(lay.cols) else lay.ntiles)
+                  for n, j in enumerate(lay.cols)}
+
+        def post_panel(k: int, ev_panel) -> None:
+            if k in bounds and bounds[k][1] > bounds[k][0]:
+                lo, hi = bounds[k]
+                self.s_copy.wait_event(ev_panel)
+                with torch.cuda.stream(self.s_copy):
+                    host_out[lo:hi].copy_(self.A.buf[lo:hi], non_blocking=True)
+
+        self._run(self.d_tasks.data_ptr(), factor=True, post_panel=post_panel)
+        cur.wait_stream(self.s_copy)
 
     def info(self) -> int:
         """LAPACK info of the last factor(): 0, or the 1-based global index of the first

@@ -1,6 +1,7 @@
 // chol_abi.cu — the C ABI of libchol_b200.so (see include/chol_b200.h for the contract and
 // the reference interfaces each entry point replaces).  Host code here only validates
 // arguments and enqueues kernels; there is no CPU arithmetic and no CPU fallback.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -16,6 +17,7 @@ using namespace chol;
 namespace {
 
 thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};  // kernels enqueued by this library (chol_launch_count)
 std::mutex g_mu;
 bool g_inited[64] = {false};
 
@@ -31,6 +33,7 @@ int fail_arg(int idx, const char* fn, const char* what) {
     do {                                                         \
         cudaError_t e__ = cudaGetLastError();                    \
         if (e__ != cudaSuccess) return fail_cuda(e__, where);    \
+        g_launches.fetch_add(1, std::memory_order_relaxed);      \
     } while (0)
 
 int ensure_init() {
@@ -60,8 +63,11 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Enqueue the grouped update.  `fast_ok_ptrs` tells whether the caller vouches for the
 // 16-byte alignment of the tile pointers of a device task list (single tasks are checked).
+// `inplace_tri`: the tasks have C == A, beta == 0 and B lower triangular (the multiply step of
+// the blocked TRSM); the fast path handles the aliasing (one CTA column, n <= BN), the generic
+// path needs the alias-safe kernel.
 int launch_gemm(const chol_task_t* d_tasks, const chol_task_t* one, int ntasks, int m, int n, int k, int lda,
-                int ldb, int ldc, double alpha, double beta, cudaStream_t st) {
+                int ldb, int ldc, double alpha, double beta, cudaStream_t st, bool inplace_tri = false) {
     if (ntasks <= 0 || m <= 0 || n <= 0) return 0;
     GemmParams p;
     memset(&p, 0, sizeof(p));
@@ -81,6 +87,14 @@ int launch_gemm(const chol_task_t* d_tasks, const chol_task_t* one, int ntasks, 
         if (grid > 0x7fffffffLL) return fail_arg(2, "chol_gemm_tasks", "too many CTA tiles");
         gemm_nt_dmma_kernel<<<dim3((unsigned)grid), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
         CHECK_LAUNCH("gemm_nt_dmma_kernel");
+    } else if (inplace_tri) {
+        for (int t0 = 0; t0 < ntasks; t0 += 32768) {
+            GemmParams q = p;
+            const int cnt = (ntasks - t0 < 32768) ? ntasks - t0 : 32768;
+            if (d_tasks) q.tasks = d_tasks + t0;
+            trmm_rlt_inplace_generic_kernel<<<dim3((m + 127) / 128, cnt), 128, 0, st>>>(q);
+            CHECK_LAUNCH("trmm_rlt_inplace_generic_kernel");
+        }
     } else {
         dim3 blk(32, 8);
         for (int t0 = 0; t0 < ntasks; t0 += 32768) {
@@ -122,7 +136,7 @@ int trsm_sweep(int b, const double* L, int ldl, const double* Winv, double* cons
                 if (rc) return rc;
             }
             t.C = single + size_t(o) * lda; t.A = t.C; t.B = Wj; t.flags = 0;
-            int rc = launch_gemm(nullptr, &t, 1, b, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st);
+            int rc = launch_gemm(nullptr, &t, 1, b, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
             if (rc) return rc;
         } else {
             chol_task_t* upd = scratch;
@@ -133,7 +147,7 @@ int trsm_sweep(int b, const double* L, int ldl, const double* Winv, double* cons
                 int rc = launch_gemm(upd, nullptr, ntiles, b, nbv, o, lda, ldl, lda, -1.0, 1.0, st);
                 if (rc) return rc;
             }
-            int rc = launch_gemm(mul, nullptr, ntiles, b, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st);
+            int rc = launch_gemm(mul, nullptr, ntiles, b, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
             if (rc) return rc;
         }
     }
@@ -152,6 +166,7 @@ int chol_init(int device) {
 int chol_finalize(void) { return 0; }
 const char* chol_last_error(void) { return g_err.c_str(); }
 const char* chol_version(void) { return "chol_b200 0.1 sm_100a"; }
+unsigned long long chol_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int chol_gemm_tasks(const chol_task_t* d_tasks, int ntasks, int m, int n, int k, int lda, int ldb, int ldc,
                     double alpha, double beta, void* stream) {
@@ -193,7 +208,7 @@ int chol_potrf_tile(int b, double* A, int lda, double* work, int* d_info, int in
             chol_task_t t;
             // rows below the diagonal block: X = A * inv(L_jj)^T (in place; each CTA owns its rows)
             t.C = Ajj + nbv; t.A = t.C; t.B = Wj; t.flags = 0;
-            int rc = launch_gemm(nullptr, &t, 1, rem, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st);
+            int rc = launch_gemm(nullptr, &t, 1, rem, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
             if (rc) return rc;
             // trailing lower triangle: A22 -= X * X^T
             t.C = A + size_t(o + nbv) * lda + (o + nbv); t.A = Ajj + nbv; t.B = t.A; t.flags = CHOL_TASK_LOWER;

@@ -276,4 +276,19 @@ __global__ void gemm_nt_generic_kernel(const GemmParams p) {
     *c = v;
 }
 
+// In-place right multiplication by the transpose of a lower-triangular matrix, for the shapes
+// the fast path cannot take:  A <- A * W^T  (A m x n, W n x n lower).  Column j of the result
+// needs columns l <= j of A only, so one thread per row sweeping j downwards is alias-safe.
+__global__ void trmm_rlt_inplace_generic_kernel(const GemmParams p) {
+    chol_task_t task = p.tasks ? p.tasks[blockIdx.y] : p.one;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.m) return;
+    double* a = task.C + i;
+    for (int j = p.n - 1; j >= 0; --j) {
+        double s = 0.0;
+        for (int l = 0; l <= j && l < p.k; ++l) s = fma(a[size_t(l) * p.ldc], task.B[size_t(l) * p.ldb + j], s);
+        a[size_t(j) * p.ldc] = p.alpha * s;
+    }
+}
+
 }  // namespace chol

@@ -1,0 +1,58 @@
+"""Process / device setup: the CHAMELEON_Init(ncpu, ngpu) / CHAMELEON_Finalize pair (v6_test.c:41,93;
+worker_distrib.cpp:584-589) for one process per B200.
+
+Under ``torch.distributed.run`` (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* in the environment) it
+binds the process to its GPU and creates the NCCL process group used for the panel broadcasts,
+with high-priority communication streams so the broadcast kernels are not queued behind the
+trailing-update grid.
+"""
+from __future__ import annotations
+
+import datetime
+import os
+
+import torch
+
+from . import _lib
+
+_state = {"inited": False, "rank": 0, "world": 1, "device": None}
+
+
+def env_int(key: str, default: int) -> int:
+    """env_int (worker_distrib.cpp:82-85): non-negative integer from the environment."""
+    try:
+        return max(0, int(os.environ[key]))
+    except (KeyError, ValueError):
+        return default
+
+
+def init(ncpu: int = 0, ngpu: int | None = None) -> tuple[int, int]:
+    """Returns (rank, world).  `ncpu` is accepted for signature parity and ignored (no CPU
+    workers exist); `ngpu` defaults to env CHM_NGPU (worker_distrib.cpp:585) or WORLD_SIZE."""
+    if _state["inited"]:
+        return _state["rank"], _state["world"]
+    if not torch.cuda.is_available():
+        raise RuntimeError("dense-linear-app_b200 needs a CUDA device (B200): there is no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    _lib.call("chol_init", local)
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", rank=rank, world_size=world, pg_options=opts,
+                                    timeout=datetime.timedelta(seconds=600),
+                                    device_id=torch.device("cuda", local))
+    _state.update(inited=True, rank=rank, world=world, device=torch.device("cuda", local))
+    return rank, world
+
+
+def finalize() -> None:
+    """CHAMELEON_Finalize (v6_test.c:93)."""
+    if _state["inited"] and _state["world"] > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    _state["inited"] = False

@@ -46,6 +46,10 @@ const char* chol_last_error(void);
 /* Library version string, e.g. "chol_b200 0.1 sm_100a". */
 const char* chol_version(void);
 
+/* Number of CUDA kernels this library has enqueued so far in the process (all threads); the
+ * benchmark reports the difference over its timed region. */
+unsigned long long chol_launch_count(void);
+
 /* ---- grouped rank-K update: the hot kernel (K4/K5 of SURVEY 2b) ------------------ */
 
 /* One C-tile update  C <- beta*C + alpha * A * B^T  (A: m x k, B: n x k, col-major).

@@ -1,0 +1,196 @@
+"""Whole-matrix path on the GPU: TiledCholesky / potrf_tile_desc (replaces CHAMELEON_dpotrf_Tile,
+v6_test.c:56) against the oracle's tile DAG and monolithic dpotrf; generator parity; batched
+POTRF; worker Execute; the v6_test command line.  Gates (north_star): backward error
+||A - L L^T||_F/||A||_F <= 1e-13; |L - Lref| <= 1e-10 * max(|Lref|, 1e-3 * max|Lref|)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def element_gate(L, Lref):
+    floor = 1e-3 * np.abs(Lref).max()
+    return np.all(np.abs(L - Lref) <= 1e-10 * np.maximum(np.abs(Lref), floor))
+
+
+@pytest.mark.parametrize("N,b", [(64, 16), (96, 32), (256, 64), (1000, 128), (1024, 256), (2048, 512)])
+def test_generator_matches_oracle_bit_exact(cuda_lib, oracle, N, b):
+    from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+    M = TileMatrix(TileDesc.square(N, b)).generate(float(N), 42)
+    got = M.to_numpy()
+    ref = oracle.plgsy(float(N), N, 42) if N <= 1024 else oracle.plgsy_numpy(float(N), N, 42)
+    assert np.array_equal(np.tril(got), np.tril(ref))
+    # diagonal tiles are generated whole (mirrored upper part)
+    assert np.array_equal(got[:b, :b], ref[:b, :b])
+
+
+@pytest.mark.parametrize("N,b,lookahead", [(4, 4, True), (12, 4, True), (64, 16, False), (200, 64, True),
+                                           (1000, 128, True), (1024, 256, False), (2048, 512, True),
+                                           (4096, 512, True)])
+def test_factor_matches_oracle(cuda_lib, oracle, N, b, lookahead):
+    """configs[0] of BASELINE.json is the last case: N=4096, tile 512."""
+    from scipy.linalg import lapack
+    from dense_linear_app_b200.cholesky import TiledCholesky
+    from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+    A = oracle.plgsy(float(N), N, 42) if N <= 1024 else oracle.plgsy_numpy(float(N), N, 42)
+    M = TileMatrix(TileDesc.square(N, b)).from_numpy(A)
+    M0 = M.clone()
+    ch = TiledCholesky(M, lookahead=lookahead)
+    ch.factor()
+    assert ch.info() == 0
+    L = np.tril(M.to_numpy())
+    if N <= 256 and N % b == 0:
+        t = oracle.to_tiles(A, b)                      # plain-C restatement of the same tile DAG
+        assert oracle.potrf_tiled(t, N // b, b) == 0
+        Lref = np.tril(oracle.from_tiles(t, N // b, b))
+    else:
+        Lref, info = lapack.dpotrf(A, lower=1, clean=1)   # OpenBLAS: the reference's library
+        assert info == 0
+    assert element_gate(L, Lref)
+    assert np.abs(L - Lref).max() <= 1e-13 * np.abs(Lref).max()
+    bwd = np.linalg.norm(L @ L.T - A) / np.linalg.norm(A)
+    assert bwd <= 1e-13
+    res = ch.residual(M0)                               # device-side residual agrees with the host one
+    assert res["fro"] <= 1e-13 and abs(res["fro"] - bwd) <= 2e-16 + 0.2 * bwd
+    assert res["inf"] <= 1e-13
+
+
+def test_potrf_tile_desc_entry_point_and_info(cuda_lib, oracle):
+    from dense_linear_app_b200.cholesky import potrf_tile_desc
+    from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+    N, b = 512, 128
+    A = oracle.plgsy(float(N), N, 1)
+    assert potrf_tile_desc("L", TileMatrix(TileDesc.square(N, b)).from_numpy(A)) == 0
+    A[300, 300] = -4.0
+    assert potrf_tile_desc("L", TileMatrix(TileDesc.square(N, b)).from_numpy(A)) == 301   # global LAPACK index
+    with pytest.raises(ValueError):
+        potrf_tile_desc("U", TileMatrix(TileDesc.square(N, b)).from_numpy(A))
+
+
+def test_strict_upper_of_diagonal_tiles_untouched(cuda_lib, oracle):
+    from dense_linear_app_b200.cholesky import TiledCholesky
+    from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+    N, b = 512, 128
+    M = TileMatrix(TileDesc.square(N, b)).generate(float(N), 9)
+    before = M.to_numpy()
+    ch = TiledCholesky(M)
+    ch.factor()
+    assert ch.info() == 0
+    after = M.to_numpy()
+    for k in range(N // b):
+        s = slice(k * b, (k + 1) * b)
+        assert np.array_equal(np.triu(after[s, s], 1), np.triu(before[s, s], 1))
+
+
+def test_config2_properties_full_size(cuda_lib):
+    """BASELINE configs[1] (N=16384, tile 1024): too big for a CPU factor inside the test budget, so
+    check size-independent properties: info == 0, device backward error <= 1e-13, and the leading
+    2048 block equals the oracle-checked factor of the leading block (chol(A)[:m,:m] = chol(A[:m,:m]))."""
+    from scipy.linalg import lapack
+    from dense_linear_app_b200.cholesky import TiledCholesky
+    from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+    N, b, m = 16384, 1024, 2048
+    M = TileMatrix(TileDesc.square(N, b)).generate(float(N), 42)
+    lead = np.zeros((m, m))
+    for i in range(m // b):
+        for j in range(i + 1):
+            lead[i * b:(i + 1) * b, j * b:(j + 1) * b] = M.tile(i, j).cpu().numpy().T
+    lead = np.tril(lead) + np.tril(lead, -1).T
+    M0 = M.clone()
+    ch = TiledCholesky(M)
+    ch.factor()
+    assert ch.info() == 0
+    Lref, info = lapack.dpotrf(lead, lower=1, clean=1)
+    got = np.zeros((m, m))
+    for i in range(m // b):
+        for j in range(i + 1):
+            got[i * b:(i + 1) * b, j * b:(j + 1) * b] = M.tile(i, j).cpu().numpy().T
+    assert element_gate(np.tril(got), Lref)
+    res = ch.residual(M0)
+    assert res["fro"] <= 1e-13 and res["inf"] <= 1e-13
+
+
+@pytest.mark.parametrize("n,batch", [(1, 3), (5, 7), (32, 64), (128, 33), (200, 5), (256, 40)])
+def test_potrf_batched(cuda_lib, oracle, n, batch):
+    """configs[4] shape (many small SPD matrices, n=256) at a test-sized batch."""
+    from dense_linear_app_b200 import tile_ops
+    mats = [oracle.plgsy(float(n), n, 42 + i) for i in range(batch)]
+    mats[batch // 2] = mats[batch // 2].copy()
+    bad = n // 2
+    mats[batch // 2][bad, bad] = -1.0
+    d = torch.from_numpy(np.stack([np.ascontiguousarray(m.T) for m in mats])).cuda()
+    info = tile_ops.potrf_batched(d).cpu().numpy()
+    out = d.cpu().numpy()
+    for i, m in enumerate(mats):
+        ref = m.copy(order="F")
+        want = oracle.potrf_tile(ref)
+        assert info[i] == want
+        if want == 0:
+            got = out[i].T
+            assert np.abs(np.tril(got) - np.tril(ref)).max() <= 1e-13 * np.abs(ref).max()
+            assert np.array_equal(np.triu(got, 1), np.triu(m, 1))
+
+
+def test_worker_execute_runs_the_client_dag(cuda_lib, oracle):
+    """ArmoniK path end to end: client wave loop (dag.run_waves) -> JSON payload + host blobs ->
+    DagCholeskyWorker.Execute on the GPU -> blobs; result == dpotrf."""
+    from dense_linear_app_b200 import dag, worker
+    N, B = 48, 16
+    A = dag.enforce_strict_diag_dominance(dag.make_spd_like_chameleon(N))
+    nb = N // B
+    blocks = {dag.block_id_from_ij(i, j): dag.extract_block(A, B, i, j).tobytes(order="F")
+              for i in range(nb) for j in range(i + 1)}
+    out = dag.run_waves(N, B, blocks, worker.execute)
+    L = np.zeros((N, N))
+    for i in range(nb):
+        for j in range(i + 1):
+            L[i * B:(i + 1) * B, j * B:(j + 1) * B] = np.frombuffer(out[dag.block_id_from_ij(i, j)]).reshape(B, B).T
+    L = np.tril(L)
+    ref = A.copy(order="F")
+    assert oracle.potrf_tile(ref) == 0
+    assert np.abs(L - np.tril(ref)).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_worker_error_statuses(cuda_lib):
+    """Same status texts as worker_distrib.cpp:194-195,218-220,243-244,547-549,558-560."""
+    from dense_linear_app_b200 import worker
+    w = worker.DagCholeskyWorker()
+    B = 4
+    good = np.eye(B).tobytes()
+    st = w.Execute(worker.TaskHandler(json.dumps({"op": "POTRF", "B": B, "in": "x"}), {}))
+    assert not st.ok and st.details == "[Worker][POTF] Missing dependency: x"
+    st = w.Execute(worker.TaskHandler(json.dumps({"op": "GEMM", "B": B, "inC": "c", "inAi": "a", "inAj": "b"}),
+                                      {"c": good, "a": good}))
+    assert st.details == "[Worker][GEMM] Missing dependency: b"
+    st = w.Execute(worker.TaskHandler(json.dumps({"op": "POTRF", "B": B, "in": "x"}), {"x": good[:-8]}))
+    assert st.details == "[Worker][POTF] Bad block size: expected 16 doubles, got 15"
+    st = w.Execute(worker.TaskHandler(json.dumps({"op": "LU", "B": B}), {}))
+    assert st.details == "Unknown op=LU"
+    notpd = -np.eye(B)
+    st = w.Execute(worker.TaskHandler(json.dumps({"op": "POTRF", "B": B, "in": "x"}), {"x": notpd.tobytes()}))
+    assert st.details == "Exception: [Worker][POTF] dpotrf info=1"
+    st = w.Execute(worker.TaskHandler("{not json", {}))
+    assert not st.ok and st.details.startswith("Exception: ")
+    th = worker.TaskHandler(json.dumps({"op": "POTRF", "B": B, "in": "x"}), {"x": (4 * np.eye(B)).tobytes()},
+                            expected_results=["out-1"])
+    assert w.Execute(th).ok and np.array_equal(np.frombuffer(th.results["out-1"]).reshape(B, B), 2 * np.eye(B))
+
+
+def test_v6_test_command_line(cuda_lib):
+    """The driver contract benchmark.c relies on: 16 positionals, the two parsed stdout lines, exit 0."""
+    from dense_linear_app_b200 import bench_sweep
+    args = bench_sweep.driver_argv(0, 1, 1000, 128, 1, 1, 42)
+    pr = subprocess.run([sys.executable, "-m", "dense_linear_app_b200.v6_test"] + args, cwd=ROOT,
+                        capture_output=True, text=True, timeout=600)
+    assert pr.returncode == 0, pr.stderr
+    gflops, rel = bench_sweep.parse_metrics(pr.stdout)
+    assert gflops > 0 and 0 <= rel < 1e-10
+    assert "[setup] ncpu=0 ngpu=1 N=1000 NB=128" in pr.stdout and "N = 1000, NB = 128" in pr.stdout
+    assert "PASS" in pr.stdout
