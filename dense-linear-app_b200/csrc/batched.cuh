@@ -6,24 +6,23 @@
 
 namespace chol {
 
-// n <= 128: whole matrix resident in shared memory.
+// n <= 128: whole matrix resident in shared memory, factored with the warp-level recursive
+// block Cholesky of panel.cuh.
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_batched_smem_kernel(int n, double* __restrict__ Abase, int lda, long long stride, int* __restrict__ d_info) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* S = reinterpret_cast<double*>(smem_raw);
     __shared__ int s_info;
+    const DiagSmem m = diag_smem(smem_raw);
     double* A = Abase + size_t(blockIdx.x) * stride;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int j = idx / n, i = idx - j * n;
-        S[j * DPITCH + i] = (i >= j) ? A[size_t(j) * lda + i] : 0.0;
-    }
+    const int n32 = (n + SB - 1) / SB * SB;
+    diag_load(m.S, A, lda, n, n32);
     __syncthreads();
-    const int info = potrf_smem(S, n, &s_info);
+    const int info = potrf_block_smem(m, n32, &s_info);
     if (tid == 0) d_info[blockIdx.x] = info;
     for (int idx = tid; idx < n * n; idx += nt) {
         const int j = idx / n, i = idx - j * n;
-        if (i >= j) A[size_t(j) * lda + i] = S[j * DPITCH + i];
+        if (i >= j) A[size_t(j) * lda + i] = m.S[j * DPITCH + i];
     }
 }
 

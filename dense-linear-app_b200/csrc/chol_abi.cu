@@ -3,6 +3,7 @@
 // arguments and enqueues kernels; there is no CPU arithmetic and no CPU fallback.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -19,6 +20,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};  // kernels enqueued by this library (chol_launch_count)
 std::mutex g_mu;
+bool g_force_wide = false;  // CHOL_GEMM_WIDE=1: use the 128x128 shape everywhere (A/B experiments)
 bool g_inited[64] = {false};
 
 int fail_cuda(cudaError_t e, const char* where) {
@@ -43,8 +45,16 @@ int ensure_init() {
     if (dev < 0 || dev >= 64) return fail_arg(1, "chol_init", "device index");
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_inited[dev]) return 0;
-    e = cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(GEMM_SMEM_BYTES));
-    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(gemm_nt_dmma_kernel)");
+    if (const char* w = getenv("CHOL_GEMM_WIDE")) g_force_wide = (w[0] == '1');
+    e = cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmWide>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(GemmWide::SMEM_BYTES));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmWide>)");
+    e = cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(GemmPair::SMEM_BYTES));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmPair>)");
+    e = cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmPair>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(carveout)");
     e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DIAG_SMEM_BYTES));
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_diag_kernel)");
     e = cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(DIAG_SMEM_BYTES));
@@ -81,11 +91,18 @@ int launch_gemm(const chol_task_t* d_tasks, const chol_task_t* one, int ntasks, 
                 (ldc % 2 == 0);
     if (fast && one) fast = aligned16(one->A) && aligned16(one->B) && aligned16(one->C);
     if (fast) {
+        // In-place multiplies need all n (<= 128) columns of a row block in one CTA: wide shape.
+        const bool wide = inplace_tri || g_force_wide;
+        const int bn = wide ? GemmWide::BN : GemmPair::BN;
+        if (inplace_tri && n > GemmWide::BN) return fail_arg(4, "launch_gemm", "in-place multiply wider than one CTA");
         p.nbm = (m + BM - 1) / BM;
-        p.nbn = (n + BN - 1) / BN;
+        p.nbn = (n + bn - 1) / bn;
         const long long grid = (long long)ntasks * p.nbm * p.nbn;
         if (grid > 0x7fffffffLL) return fail_arg(2, "chol_gemm_tasks", "too many CTA tiles");
-        gemm_nt_dmma_kernel<<<dim3((unsigned)grid), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(p);
+        if (wide)
+            gemm_nt_dmma_kernel<GemmWide><<<dim3((unsigned)grid), GemmWide::THREADS, GemmWide::SMEM_BYTES, st>>>(p);
+        else
+            gemm_nt_dmma_kernel<GemmPair><<<dim3((unsigned)grid), GemmPair::THREADS, GemmPair::SMEM_BYTES, st>>>(p);
         CHECK_LAUNCH("gemm_nt_dmma_kernel");
     } else if (inplace_tri) {
         for (int t0 = 0; t0 < ntasks; t0 += 32768) {

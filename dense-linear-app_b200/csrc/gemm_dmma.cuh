@@ -30,14 +30,31 @@
 
 namespace chol {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 6;
-constexpr int PITCH = BM + 4;                       // doubles per slab column in smem
-constexpr int SLAB_DOUBLES = BK * PITCH;            // one operand slab
-constexpr int STAGE_DOUBLES = 2 * SLAB_DOUBLES;     // A slab + B slab
-constexpr int GEMM_CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;
-constexpr size_t GEMM_SMEM_BYTES = size_t(STAGES) * STAGE_DOUBLES * 8 + 2 * STAGES * 8 + 16;
+constexpr int BM = 128, BK = 16;
+constexpr int PITCH = BM + 4;                       // doubles per A slab column in smem
+
+// Two shapes of the same kernel:
+//   GemmWide   128x128 CTA tile, 8 consumer warps, 1 CTA/SM  - the in-place multiply steps of the
+//              blocked TRSM/POTRF (they need the whole 128-column block in ONE CTA, see launch_gemm);
+//   GemmPair   128x64 CTA tile, 4 consumer warps, 2 CTAs/SM  - the trailing update: while one CTA
+//              reads/writes its C block (epilogue) or fills its pipeline, the co-resident CTA
+//              keeps the DMMA pipe busy (one warp per SM sub-partition saturates it).
+template <int BN_, int STAGES_, int MIN_CTAS_>
+struct GemmCfg {
+    static constexpr int BN = BN_;
+    static constexpr int STAGES = STAGES_;
+    static constexpr int MIN_CTAS = MIN_CTAS_;
+    static constexpr int WARPS_N = BN_ / 32;
+    static constexpr int CONSUMER_WARPS = 2 * WARPS_N;
+    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+    static constexpr int PITCH_B = BN_ + 4;
+    static constexpr int SLAB_A = BK * PITCH;
+    static constexpr int SLAB_B = BK * PITCH_B;
+    static constexpr int STAGE_DOUBLES = SLAB_A + SLAB_B;
+    static constexpr size_t SMEM_BYTES = size_t(STAGES_) * STAGE_DOUBLES * 8 + 2 * STAGES_ * 8 + 16;
+};
+using GemmWide = GemmCfg<128, 6, 1>;
+using GemmPair = GemmCfg<64, 4, 2>;
 
 struct GemmParams {
     const chol_task_t* tasks;   // device array, or nullptr -> `one`
@@ -93,8 +110,12 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 // ---- the kernel --------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES, STAGE_DOUBLES = Cfg::STAGE_DOUBLES;
+    constexpr int SLAB_DOUBLES = Cfg::SLAB_A, PITCH_B = Cfg::PITCH_B;
+    constexpr int GEMM_CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(STAGES) * STAGE_DOUBLES);
     // bars[0..STAGES) = full, bars[STAGES..2*STAGES) = empty
@@ -118,9 +139,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __g
         task = p.one;
     }
     const bool lower = (task.flags & CHOL_TASK_LOWER) != 0;
-    if (lower && bn > bm) return;  // block strictly above the diagonal: nothing to do
-
     const int row0 = bm * BM, col0 = bn * BN;
+    if (lower && col0 >= row0 + BM) return;  // block strictly above the diagonal: nothing to do
+
     const int mv = min(BM, p.m - row0);  // valid rows / cols of this block
     const int nv = min(BN, p.n - col0);
     const int nk = (p.k + BK - 1) / BK;
@@ -161,7 +182,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __g
             if (lane == 0) mbar_expect_tx(full, uint32_t(kc) * uint32_t(mv + nv) * 8u);
             __syncwarp();
             if (col < kc) {
-                double* dst = smem + size_t(s) * STAGE_DOUBLES + (isA ? 0 : SLAB_DOUBLES) + col * PITCH;
+                double* dst = smem + size_t(s) * STAGE_DOUBLES + (isA ? col * PITCH : SLAB_DOUBLES + col * PITCH_B);
                 bulk_g2s(smem_u32(dst), gsrc + size_t(k0 + col) * ld, bytes, full);
             }
         }
@@ -170,7 +191,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __g
 
     // ========================= consumer warps: DMMA main loop ==========================
     const int wm = warp & 1;   // 2 warps along m (64 rows each)
-    const int wn = warp >> 1;  // 4 warps along n (32 cols each)
+    const int wn = warp >> 1;  // BN/32 warps along n (32 cols each)
     const int g = lane >> 2;   // mma group id  -> rows 2g, 2g+1 of a 16-row block
     const int t = lane & 3;    // thread in group -> k index / columns 4t..4t+3
 
@@ -186,7 +207,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __g
                 for (int np = 0; np < 2; ++np) acc[q][r][mp][np][0] = acc[q][r][mp][np][1] = 0.0;
 
     const int a_off = t * PITCH + wm * 64 + 2 * g;                  // + q*16 + kk*PITCH
-    const int b_off = SLAB_DOUBLES + t * PITCH + wn * 32 + 2 * g;   // + r*16 + kk*PITCH
+    const int b_off = SLAB_DOUBLES + t * PITCH_B + wn * 32 + 2 * g; // + r*16 + kk*PITCH_B
 
     for (int it = 0; it < nk; ++it) {
         const int s = it % STAGES;
@@ -203,7 +224,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __g
                     a[q] = *reinterpret_cast<const double2*>(st + a_off + kk * PITCH + q * 16);
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
-                    b[r] = *reinterpret_cast<const double2*>(st + b_off + kk * PITCH + r * 16);
+                    b[r] = *reinterpret_cast<const double2*>(st + b_off + kk * PITCH_B + r * 16);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -221,7 +242,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __g
 
     // ================================ epilogue ========================================
     const double alpha = p.alpha, beta = p.beta;
-    const bool diag_block = lower && (bm == bn);
+    const bool diag_block = lower && (col0 + BN > row0);   // block touches the diagonal
     double* gC = task.C + size_t(col0) * p.ldc + row0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -238,9 +259,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_nt_dmma_kernel(const __g
                     double* ptr = gC + size_t(c_loc) * p.ldc + r_loc;
                     double v0 = alpha * acc[q][r][0][np][e];
                     double v1 = alpha * acc[q][r][1][np][e];
-                    if (diag_block && r_loc < c_loc) {
+                    if (diag_block && row0 + r_loc < col0 + c_loc) {
                         // pair straddles or lies above the diagonal
-                        if (r_loc + 1 == c_loc) {
+                        if (row0 + r_loc + 1 == col0 + c_loc) {
                             if (beta != 0.0) v1 += beta * ptr[1];
                             ptr[1] = v1;
                         }
