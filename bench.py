@@ -159,6 +159,10 @@ def main_ours(a) -> int:
         return 2
     dist = torch.distributed if world > 1 else None
     g = ProcessGrid.for_world(world)
+    if os.environ.get("CHOL_GRID"):            # e.g. CHOL_GRID=2x1: experiment with another grid shape
+        gp, gq = (int(x) for x in os.environ["CHOL_GRID"].lower().split("x"))
+        assert gp * gq == world
+        g = ProcessGrid(gp, gq)
     dev = torch.device("cuda", torch.cuda.current_device())
     N, b = a.N, a.tile
     desc = TileDesc(b, b, b * b, N, N, 0, 0, N, N, g.P, g.Q)

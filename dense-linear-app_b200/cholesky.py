@@ -57,6 +57,10 @@ class TiledCholesky:
             self.panel = torch.empty((2, max(nt - 1, 1), b, b), **f64)
             self.diag = torch.empty((b, b), **f64)
         self._col_groups = None
+        if self.world > 1 and self.grid.P > 1:
+            # dist.new_group is collective over ALL ranks: create every column group here, in the
+            # same order everywhere, never lazily inside the factorization
+            self._make_column_groups()
         self.update_events = None   # set to [] to time every trailing-update launch (bench.py roofline)
         self._build_plan()
         if self.cuda:
@@ -178,18 +182,27 @@ class TiledCholesky:
         self.trsm_scratch = torch.empty(max(max_panel, 1) * 8, dtype=torch.int64, device=self.dev)
         self.n_update_tasks = off
 
+    def _make_column_groups(self) -> None:
+        import torch.distributed as dist
+        base_ranks = list(range(self.world)) if self.group is None else dist.get_process_group_ranks(self.group)
+        opts = None
+        if self.cuda:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        self._col_groups = []
+        for qq in range(self.grid.Q):
+            members = [base_ranks[self.grid.rank_of(p, qq)] for p in range(self.grid.P)]
+            self._col_groups.append(dist.new_group(members, pg_options=opts) if opts else dist.new_group(members))
+        # touch every communicator once now (NCCL may set them up lazily, which blocks the host —
+        # that must not happen in the middle of the asynchronous factorization)
+        tok = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        dist.broadcast(tok, src=base_ranks[0], group=self.group)
+        dist.broadcast(tok, src=base_ranks[self.grid.rank_of(0, self.lay.q)], group=self._col_groups[self.lay.q])
+        if self.cuda:
+            torch.cuda.synchronize(self.dev)
+
     def _column_group(self, q: int):
         """Process group of the P ranks of grid column q (for the L_kk broadcast)."""
-        if self.grid.P == 1:
-            return None
-        if self._col_groups is None:
-            import torch.distributed as dist
-            base_ranks = list(range(self.world)) if self.group is None else dist.get_process_group_ranks(self.group)
-            self._col_groups = []
-            for qq in range(self.grid.Q):  # every rank creates every group, in the same order
-                members = [base_ranks[self.grid.rank_of(p, qq)] for p in range(self.grid.P)]
-                self._col_groups.append(dist.new_group(members))
-        return self._col_groups[q]
+        return None if self.grid.P == 1 else self._col_groups[q]
 
     # ---- execution -------------------------------------------------------------------------------
     def _stream_ptr(self, s) -> int:

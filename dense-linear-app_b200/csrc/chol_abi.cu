@@ -71,27 +71,31 @@ int ensure_init() {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Enqueue the grouped update.  `fast_ok_ptrs` tells whether the caller vouches for the
-// 16-byte alignment of the tile pointers of a device task list (single tasks are checked).
-// `inplace_tri`: the tasks have C == A, beta == 0 and B lower triangular (the multiply step of
-// the blocked TRSM); the fast path handles the aliasing (one CTA column, n <= BN), the generic
-// path needs the alias-safe kernel.
-int launch_gemm(const chol_task_t* d_tasks, const chol_task_t* one, int ntasks, int m, int n, int k, int lda,
-                int ldb, int ldc, double alpha, double beta, cudaStream_t st, bool inplace_tri = false) {
-    if (ntasks <= 0 || m <= 0 || n <= 0) return 0;
+GemmParams make_params(int ntasks, int m, int n, int k, int lda, int ldb, int ldc, double alpha, double beta) {
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.tasks = d_tasks;
-    if (one) p.one = *one;
     p.ntasks = ntasks;
     p.m = m; p.n = n; p.k = k;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.alpha = alpha; p.beta = beta;
-    bool fast = (m % 2 == 0) && (n % 2 == 0) && (k % 4 == 0) && (k > 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
-                (ldc % 2 == 0);
-    if (fast && one) fast = aligned16(one->A) && aligned16(one->B) && aligned16(one->C);
+    return p;
+}
+
+// Enqueue a grouped update.  The task source is p.tasks (device list), p.tile_ptrs (panel mode)
+// or p.one (single task, whose pointers are checked for the fast path's 16-byte alignment; the
+// caller vouches for the alignment of device lists).
+// `inplace_tri`: the tasks have C == A, beta == 0 and B lower triangular (the multiply step of
+// the blocked TRSM); the fast path handles the aliasing by giving all n (<= 128) columns of a row
+// block to ONE CTA, the generic path has an alias-safe kernel.
+int launch_gemm(GemmParams p, cudaStream_t st, bool inplace_tri = false) {
+    const int ntasks = p.ntasks, m = p.m, n = p.n, k = p.k;
+    if (ntasks <= 0 || m <= 0 || n <= 0) return 0;
+    const bool single = !p.tasks && !p.tile_ptrs;
+    bool fast = (m % 2 == 0) && (n % 2 == 0) && (k % 4 == 0) && (k > 0) && (p.lda % 2 == 0) && (p.ldb % 2 == 0) &&
+                (p.ldc % 2 == 0) && (p.c_off % 2 == 0) && (p.a_off % 2 == 0);
+    if (fast && single) fast = aligned16(p.one.A) && aligned16(p.one.B) && aligned16(p.one.C);
+    if (fast && p.tile_ptrs) fast = aligned16(p.one.B);
     if (fast) {
-        // In-place multiplies need all n (<= 128) columns of a row block in one CTA: wide shape.
         const bool wide = inplace_tri || g_force_wide;
         const int bn = wide ? GemmWide::BN : GemmPair::BN;
         if (inplace_tri && n > GemmWide::BN) return fail_arg(4, "launch_gemm", "in-place multiply wider than one CTA");
@@ -104,71 +108,79 @@ int launch_gemm(const chol_task_t* d_tasks, const chol_task_t* one, int ntasks, 
         else
             gemm_nt_dmma_kernel<GemmPair><<<dim3((unsigned)grid), GemmPair::THREADS, GemmPair::SMEM_BYTES, st>>>(p);
         CHECK_LAUNCH("gemm_nt_dmma_kernel");
-    } else if (inplace_tri) {
-        for (int t0 = 0; t0 < ntasks; t0 += 32768) {
-            GemmParams q = p;
-            const int cnt = (ntasks - t0 < 32768) ? ntasks - t0 : 32768;
-            if (d_tasks) q.tasks = d_tasks + t0;
-            trmm_rlt_inplace_generic_kernel<<<dim3((m + 127) / 128, cnt), 128, 0, st>>>(q);
+        return 0;
+    }
+    for (int t0 = 0; t0 < ntasks; t0 += 32768) {
+        GemmParams q = p;
+        q.ntasks = (ntasks - t0 < 32768) ? ntasks - t0 : 32768;
+        if (p.tasks) q.tasks = p.tasks + t0;
+        if (p.tile_ptrs) q.tile_ptrs = p.tile_ptrs + t0;
+        if (inplace_tri) {
+            trmm_rlt_inplace_generic_kernel<<<dim3((m + 127) / 128, q.ntasks), 128, 0, st>>>(q);
             CHECK_LAUNCH("trmm_rlt_inplace_generic_kernel");
-        }
-    } else {
-        dim3 blk(32, 8);
-        for (int t0 = 0; t0 < ntasks; t0 += 32768) {
-            GemmParams q = p;
-            const int cnt = (ntasks - t0 < 32768) ? ntasks - t0 : 32768;
-            if (d_tasks) q.tasks = d_tasks + t0;
-            dim3 grd((m + 31) / 32, (n + 7) / 8, cnt);
-            gemm_nt_generic_kernel<<<grd, blk, 0, st>>>(q);
+        } else {
+            gemm_nt_generic_kernel<<<dim3((m + 31) / 32, (n + 7) / 8, q.ntasks), dim3(32, 8), 0, st>>>(q);
             CHECK_LAUNCH("gemm_nt_generic_kernel");
         }
     }
     return 0;
 }
 
-__global__ void build_trsm_tasks_kernel(double* const* tiles, int ntiles, int lda, int col_off, const double* Lrow,
-                                        const double* Winv, chol_task_t* upd, chol_task_t* mul) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntiles) return;
-    double* tile = tiles[i];
-    double* cblk = tile + size_t(col_off) * lda;
-    upd[i].C = cblk; upd[i].A = tile; upd[i].B = Lrow; upd[i].flags = 0;
-    mul[i].C = cblk; mul[i].A = cblk; mul[i].B = Winv; mul[i].flags = 0;
+int launch_one(const chol_task_t& t, int m, int n, int k, int lda, int ldb, int ldc, double alpha, double beta,
+               cudaStream_t st, bool inplace_tri = false) {
+    GemmParams p = make_params(1, m, n, k, lda, ldb, ldc, alpha, beta);
+    p.one = t;
+    return launch_gemm(p, st, inplace_tri);
 }
 
-// X * L^T = A  for every tile, block column by block column (block size NBD):
-//   X_j = (A_j - sum_{l<j} X_l * L_jl^T) * inv(L_jj)^T
-int trsm_sweep(int b, const double* L, int ldl, const double* Winv, double* const* d_tiles, double* single,
-               int ntiles, int lda, chol_task_t* scratch, cudaStream_t st) {
-    const int nblk = (b + NBD - 1) / NBD;
-    for (int j = 0; j < nblk; ++j) {
-        const int o = j * NBD;
-        const int nbv = (b - o < NBD) ? b - o : NBD;
-        const double* Wj = Winv + size_t(j) * NBD * NBD;
-        if (single) {
-            chol_task_t t;
-            if (j > 0) {
-                t.C = single + size_t(o) * lda; t.A = single; t.B = L + o; t.flags = 0;
-                int rc = launch_gemm(nullptr, &t, 1, b, nbv, o, lda, ldl, lda, -1.0, 1.0, st);
-                if (rc) return rc;
-            }
-            t.C = single + size_t(o) * lda; t.A = t.C; t.B = Wj; t.flags = 0;
-            int rc = launch_gemm(nullptr, &t, 1, b, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
-            if (rc) return rc;
-        } else {
-            chol_task_t* upd = scratch;
-            chol_task_t* mul = scratch + ntiles;
-            build_trsm_tasks_kernel<<<(ntiles + 127) / 128, 128, 0, st>>>(d_tiles, ntiles, lda, o, L + o, Wj, upd, mul);
-            CHECK_LAUNCH("build_trsm_tasks_kernel");
-            if (j > 0) {
-                int rc = launch_gemm(upd, nullptr, ntiles, b, nbv, o, lda, ldl, lda, -1.0, 1.0, st);
-                if (rc) return rc;
-            }
-            int rc = launch_gemm(mul, nullptr, ntiles, b, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
-            if (rc) return rc;
-        }
+// X * L^T = A for one tile (`single`) or every tile of a panel (`d_tiles`), recursively over the
+// 128-column blocks [lo, hi) of L:   solve(lo, mid);  A[:, mid:hi) -= X[:, lo:mid) L[mid:hi, lo:mid)^T;
+// solve(mid, hi);   a leaf multiplies by the inverted diagonal block: X_j = A_j inv(L_jj)^T.
+// Compared with a left-to-right sweep the dependent chain of GEMM K-lengths drops from
+// 128*(1+2+..+7) to 4*128 + 2*256 + 512 and the big updates expose more parallel CTAs.
+struct TrsmCtx {
+    int b;
+    const double* L;
+    int ldl;
+    const double* Winv;
+    double* const* d_tiles;
+    double* single;
+    int ntiles, lda;
+    cudaStream_t st;
+};
+
+int trsm_issue(const TrsmCtx& c, long long c_off, long long a_off, const double* B, int n, int k, int ldb,
+               double alpha, double beta, bool inplace) {
+    GemmParams p = make_params(c.ntiles, c.b, n, k, c.lda, ldb, c.lda, alpha, beta);
+    if (c.single) {
+        p.one.C = c.single + c_off; p.one.A = c.single + a_off; p.one.B = B; p.one.flags = 0;
+    } else {
+        p.tile_ptrs = c.d_tiles; p.c_off = c_off; p.a_off = a_off; p.one.B = B;
     }
-    return 0;
+    return launch_gemm(p, c.st, inplace);
+}
+
+int trsm_rec(const TrsmCtx& c, int lo, int hi) {
+    if (hi - lo == 1) {
+        const int o = lo * NBD;
+        const int nbv = (c.b - o < NBD) ? c.b - o : NBD;
+        return trsm_issue(c, (long long)o * c.lda, (long long)o * c.lda, c.Winv + size_t(lo) * NBD * NBD, nbv, nbv, NBD,
+                          1.0, 0.0, true);
+    }
+    const int mid = lo + (hi - lo + 1) / 2;
+    if (int rc = trsm_rec(c, lo, mid)) return rc;
+    const int o_lo = lo * NBD, o_mid = mid * NBD;
+    const int o_hi = (hi * NBD < c.b) ? hi * NBD : c.b;
+    if (int rc = trsm_issue(c, (long long)o_mid * c.lda, (long long)o_lo * c.lda, c.L + size_t(o_lo) * c.ldl + o_mid,
+                            o_hi - o_mid, o_mid - o_lo, c.ldl, -1.0, 1.0, false))
+        return rc;
+    return trsm_rec(c, mid, hi);
+}
+
+int trsm_sweep(int b, const double* L, int ldl, const double* Winv, double* const* d_tiles, double* single,
+               int ntiles, int lda, cudaStream_t st) {
+    TrsmCtx c{b, L, ldl, Winv, d_tiles, single, ntiles, lda, st};
+    return trsm_rec(c, 0, (b + NBD - 1) / NBD);
 }
 
 }  // namespace
@@ -196,7 +208,9 @@ int chol_gemm_tasks(const chol_task_t* d_tasks, int ntasks, int m, int n, int k,
     if (ldb < (n > 1 ? n : 1)) return fail_arg(7, "chol_gemm_tasks", "ldb");
     if (ldc < (m > 1 ? m : 1)) return fail_arg(8, "chol_gemm_tasks", "ldc");
     if (int rc = ensure_init()) return rc;
-    return launch_gemm(d_tasks, nullptr, ntasks, m, n, k, lda, ldb, ldc, alpha, beta, (cudaStream_t)stream);
+    GemmParams p = make_params(ntasks, m, n, k, lda, ldb, ldc, alpha, beta);
+    p.tasks = d_tasks;
+    return launch_gemm(p, (cudaStream_t)stream);
 }
 
 size_t chol_potrf_tile_workspace(int b) {
@@ -225,11 +239,11 @@ int chol_potrf_tile(int b, double* A, int lda, double* work, int* d_info, int in
             chol_task_t t;
             // rows below the diagonal block: X = A * inv(L_jj)^T (in place; each CTA owns its rows)
             t.C = Ajj + nbv; t.A = t.C; t.B = Wj; t.flags = 0;
-            int rc = launch_gemm(nullptr, &t, 1, rem, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
+            int rc = launch_one(t, rem, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
             if (rc) return rc;
             // trailing lower triangle: A22 -= X * X^T
             t.C = A + size_t(o + nbv) * lda + (o + nbv); t.A = Ajj + nbv; t.B = t.A; t.flags = CHOL_TASK_LOWER;
-            rc = launch_gemm(nullptr, &t, 1, rem, rem, nbv, lda, lda, lda, -1.0, 1.0, st);
+            rc = launch_one(t, rem, rem, nbv, lda, lda, lda, -1.0, 1.0, st);
             if (rc) return rc;
         }
     }
@@ -251,7 +265,7 @@ int chol_trsm_tile(int b, const double* L, int ldl, double* A, int lda, double* 
     const int nblk = (b + NBD - 1) / NBD;
     trtri_diag_kernel<<<nblk, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(b, L, ldl, work);
     CHECK_LAUNCH("trtri_diag_kernel");
-    return trsm_sweep(b, L, ldl, work, nullptr, A, 1, lda, nullptr, st);
+    return trsm_sweep(b, L, ldl, work, nullptr, A, 1, lda, st);
 }
 
 int chol_trsm_tiles(int b, const double* L, int ldl, const double* potrf_work, double* const* d_tiles, int ntiles,
@@ -264,10 +278,9 @@ int chol_trsm_tiles(int b, const double* L, int ldl, const double* potrf_work, d
     if (!potrf_work) return fail_arg(4, "chol_trsm_tiles", "potrf_work");
     if (!d_tiles) return fail_arg(5, "chol_trsm_tiles", "d_tiles");
     if (lda < b) return fail_arg(7, "chol_trsm_tiles", "lda");
-    if (!d_task_scratch) return fail_arg(8, "chol_trsm_tiles", "d_task_scratch");
     if (int rc = ensure_init()) return rc;
-    return trsm_sweep(b, L, ldl, potrf_work, d_tiles, nullptr, ntiles, lda, (chol_task_t*)d_task_scratch,
-                      (cudaStream_t)stream);
+    (void)d_task_scratch;
+    return trsm_sweep(b, L, ldl, potrf_work, d_tiles, nullptr, ntiles, lda, (cudaStream_t)stream);
 }
 
 int chol_syrk_tile(int b, const double* A, int lda, double* C, int ldc, void* stream) {
@@ -280,7 +293,7 @@ int chol_syrk_tile(int b, const double* A, int lda, double* C, int ldc, void* st
     if (int rc = ensure_init()) return rc;
     chol_task_t t;
     t.C = C; t.A = A; t.B = A; t.flags = CHOL_TASK_LOWER;
-    return launch_gemm(nullptr, &t, 1, b, b, b, lda, lda, ldc, -1.0, 1.0, (cudaStream_t)stream);
+    return launch_one(t, b, b, b, lda, lda, ldc, -1.0, 1.0, (cudaStream_t)stream);
 }
 
 int chol_gemm_tile(int b, const double* Ai, int ldai, const double* Aj, int ldaj, double* C, int ldc, void* stream) {
@@ -295,7 +308,7 @@ int chol_gemm_tile(int b, const double* Ai, int ldai, const double* Aj, int ldaj
     if (int rc = ensure_init()) return rc;
     chol_task_t t;
     t.C = C; t.A = Ai; t.B = Aj; t.flags = 0;
-    return launch_gemm(nullptr, &t, 1, b, b, b, ldai, ldaj, ldc, -1.0, 1.0, (cudaStream_t)stream);
+    return launch_one(t, b, b, b, ldai, ldaj, ldc, -1.0, 1.0, (cudaStream_t)stream);
 }
 
 int chol_potrf_batched(int n, int batch, double* A, int lda, long long stride, int* d_info, void* stream) {

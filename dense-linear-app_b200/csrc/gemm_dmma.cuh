@@ -57,7 +57,11 @@ using GemmWide = GemmCfg<128, 6, 1>;
 using GemmPair = GemmCfg<64, 4, 2>;
 
 struct GemmParams {
-    const chol_task_t* tasks;   // device array, or nullptr -> `one`
+    const chol_task_t* tasks;   // device array, or nullptr -> `tile_ptrs` / `one`
+    // panel mode (blocked TRSM over a list of tiles): task t is C = tile[t] + c_off,
+    // A = tile[t] + a_off, B = one.B, flags = 0 — no task list has to be materialised
+    double* const* tile_ptrs;
+    long long c_off, a_off;
     chol_task_t one;
     int ntasks;
     int m, n, k;
@@ -109,6 +113,28 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ chol_task_t load_task(const GemmParams& p, int task_id) {
+    chol_task_t task;
+    if (p.tasks) {
+        // 32-byte task record, two 16-byte loads
+        const int4* tp = reinterpret_cast<const int4*>(p.tasks + task_id);
+        int4 lo = __ldg(tp), hi = __ldg(tp + 1);
+        task.C = reinterpret_cast<double*>((uint64_t(uint32_t(lo.y)) << 32) | uint32_t(lo.x));
+        task.A = reinterpret_cast<const double*>((uint64_t(uint32_t(lo.w)) << 32) | uint32_t(lo.z));
+        task.B = reinterpret_cast<const double*>((uint64_t(uint32_t(hi.y)) << 32) | uint32_t(hi.x));
+        task.flags = (int64_t(hi.w) << 32) | uint32_t(hi.z);
+    } else if (p.tile_ptrs) {
+        double* tile = p.tile_ptrs[task_id];
+        task.C = tile + p.c_off;
+        task.A = tile + p.a_off;
+        task.B = p.one.B;
+        task.flags = 0;
+    } else {
+        task = p.one;
+    }
+    return task;
+}
+
 // ---- the kernel --------------------------------------------------------------------
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
@@ -126,18 +152,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
     const int bm = sub % p.nbm;
     const int bn = sub / p.nbm;
 
-    chol_task_t task;
-    if (p.tasks) {
-        // 32-byte task record, two 16-byte loads
-        const int4* tp = reinterpret_cast<const int4*>(p.tasks + task_id);
-        int4 lo = __ldg(tp), hi = __ldg(tp + 1);
-        task.C = reinterpret_cast<double*>((uint64_t(uint32_t(lo.y)) << 32) | uint32_t(lo.x));
-        task.A = reinterpret_cast<const double*>((uint64_t(uint32_t(lo.w)) << 32) | uint32_t(lo.z));
-        task.B = reinterpret_cast<const double*>((uint64_t(uint32_t(hi.y)) << 32) | uint32_t(hi.x));
-        task.flags = (int64_t(hi.w) << 32) | uint32_t(hi.z);
-    } else {
-        task = p.one;
-    }
+    const chol_task_t task = load_task(p, task_id);
     const bool lower = (task.flags & CHOL_TASK_LOWER) != 0;
     const int row0 = bm * BM, col0 = bn * BN;
     if (lower && col0 >= row0 + BM) return;  // block strictly above the diagonal: nothing to do
@@ -283,7 +298,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
 // client's default B=4, C2:350) where speed is irrelevant; still GPU code, never the CPU.
 __global__ void gemm_nt_generic_kernel(const GemmParams p) {
     const int task_id = blockIdx.z;
-    chol_task_t task = p.tasks ? p.tasks[task_id] : p.one;
+    const chol_task_t task = load_task(p, task_id);
     const bool lower = (task.flags & CHOL_TASK_LOWER) != 0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -301,7 +316,7 @@ __global__ void gemm_nt_generic_kernel(const GemmParams p) {
 // the fast path cannot take:  A <- A * W^T  (A m x n, W n x n lower).  Column j of the result
 // needs columns l <= j of A only, so one thread per row sweeping j downwards is alias-safe.
 __global__ void trmm_rlt_inplace_generic_kernel(const GemmParams p) {
-    chol_task_t task = p.tasks ? p.tasks[blockIdx.y] : p.one;
+    const chol_task_t task = load_task(p, blockIdx.y);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.m) return;
     double* a = task.C + i;

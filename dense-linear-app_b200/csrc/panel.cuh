@@ -119,7 +119,10 @@ __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
 // CTA; also leaves D[J] = inv(L_JJ) for every sub-block.  Returns LAPACK info to every thread.
 __device__ __forceinline__ int potrf_block_smem(const DiagSmem& m, int n32, int* s_info) {
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    // warp index obtained through a shuffle: tells the compiler it is warp-uniform, so the
+    // `warp == 0` branch below is convergent and the shuffles inside it are emitted bare
+    // (without it ptxas wraps each one in WARPSYNC/ENDCOLLECTIVE: 30k vs 13k SASS lines)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     double* S = m.S;
     if (tid == 0) *s_info = 0;
     __syncthreads();

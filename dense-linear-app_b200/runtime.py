@@ -43,7 +43,7 @@ def init(ncpu: int = 0, ngpu: int | None = None) -> tuple[int, int]:
         if not dist.is_initialized():
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
             dist.init_process_group("nccl", rank=rank, world_size=world, pg_options=opts,
-                                    timeout=datetime.timedelta(seconds=600),
+                                    timeout=datetime.timedelta(seconds=int(os.environ.get("CHOL_NCCL_TIMEOUT_S", "300"))),
                                     device_id=torch.device("cuda", local))
     _state.update(inited=True, rank=rank, world=world, device=torch.device("cuda", local))
     return rank, world

@@ -161,3 +161,39 @@ def test_tile_ops_reject_cpu_tensors():
     with pytest.raises(_lib.CholError):
         tile_ops.gemm_tile(torch.eye(4, dtype=torch.float64), torch.eye(4, dtype=torch.float64),
                            torch.eye(4, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("b,m", [(64, 3), (200, 2), (256, 5), (384, 1), (1024, 2)])
+def test_trsm_panel_form_matches_single_tile_op(cuda_lib, oracle, b, m):
+    """chol_potrf_tile leaves the inverted diagonal blocks in `work`; chol_trsm_tiles (the whole
+    panel in one launch sequence, the TRSM loop of one wave, client_distrib.cpp v1:295-303) must
+    give exactly what the stateless single-tile op gives, and both must match the oracle."""
+    from dense_linear_app_b200 import _lib, tile_ops
+    lib = _lib.load()
+    Ai, _, _ = tiles(b, 500 + b)
+    S = np.asfortranarray(Ai @ Ai.T + b * np.eye(b))
+    dS = dev_cm(S)
+    work = torch.empty(max(lib.chol_potrf_tile_workspace(b) // 8, 1), dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("chol_potrf_tile", b, dS.data_ptr(), b, work.data_ptr(), info.data_ptr(), 0, st)
+    assert int(info.item()) == 0
+    rng = np.random.default_rng(b)
+    host = [np.asfortranarray(rng.uniform(-0.5, 0.5, (b, b))) for _ in range(m)]
+    panel = torch.stack([dev_cm(h) for h in host])
+    single = panel.clone()
+    ptrs = torch.tensor([panel[i].data_ptr() for i in range(m)], dtype=torch.int64, device="cuda")
+    scratch = torch.empty(m * 8, dtype=torch.int64, device="cuda")
+    _lib.call("chol_trsm_tiles", b, dS.data_ptr(), b, work.data_ptr(), ptrs.data_ptr(), m, b, scratch.data_ptr(), st)
+    L = np.asfortranarray(np.tril(host_cm(dS)))
+    for i in range(m):
+        tile_ops.trsm_tile(dS, single[i])
+        ref = host[i].copy(order="F")
+        if b <= 256:
+            oracle.trsm_tile(L, ref)
+        else:
+            from scipy.linalg import blas
+            ref = blas.dtrsm(1.0, L, host[i], side=1, lower=1, trans_a=1, diag=0)
+        got = host_cm(panel[i])
+        assert np.abs(got - ref).max() <= TOL * max(1.0, np.abs(ref).max()) * max(1, b / 64)
+    assert torch.equal(panel, single), "panel form and single-tile form must agree bit for bit"
