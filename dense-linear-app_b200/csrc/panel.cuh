@@ -48,14 +48,28 @@ __device__ __forceinline__ DiagSmem diag_smem(unsigned char* raw) {
     return m;
 }
 
-// Load the lower triangle of the n x n block at A into S, padded to n32 = roundup(n, 32) with the identity.
+// Load the lower triangle of the n x n block at A into S, padded to n32 = roundup(n, 32) with the
+// identity.  Thread t owns row i = t % n32 and every (blockDim/n32)-th column; the global loads
+// of 8 columns are issued back to back before the first store (ncu: the straightforward
+// one-element-per-iteration loop spent 15 % of the kernel waiting on serialized load latency).
 __device__ __forceinline__ void diag_load(double* S, const double* __restrict__ A, int lda, int n, int n32) {
-    for (int idx = threadIdx.x; idx < n32 * n32; idx += blockDim.x) {
-        const int j = idx / n32, i = idx - j * n32;
-        double v;
-        if (i < n && j < n) v = (i >= j) ? A[size_t(j) * lda + i] : 0.0;
-        else v = (i == j) ? 1.0 : 0.0;
-        S[j * DPITCH + i] = v;
+    const int i = threadIdx.x % n32;
+    const int cstep = blockDim.x / n32;          // 4 (n32 = 128) .. 16 (n32 = 32)
+    const int jfirst = threadIdx.x / n32;
+    if (jfirst >= cstep) return;                 // leftover threads when n32 does not divide blockDim
+    for (int j0 = jfirst; j0 < n32; j0 += 8 * cstep) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * cstep;
+            v[u] = (j < n32 && i == j) ? 1.0 : 0.0;
+            if (i < n && j < n && i >= j) v[u] = A[size_t(j) * lda + i];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * cstep;
+            if (j < n32) S[j * DPITCH + i] = v[u];
+        }
     }
 }
 
