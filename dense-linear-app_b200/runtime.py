@@ -39,6 +39,9 @@ def init(ncpu: int = 0, ngpu: int | None = None) -> tuple[int, int]:
     torch.cuda.set_device(local)
     _lib.call("chol_init", local)
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...", when NCCL_DEBUG is set) to stdout by default;
+        # stdout carries the driver's parsed lines (v6_test.c:64,86) / bench.py's JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         if not dist.is_initialized():
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
