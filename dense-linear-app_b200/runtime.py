@@ -41,7 +41,11 @@ def init(ncpu: int = 0, ngpu: int | None = None) -> tuple[int, int]:
     if world > 1:
         # NCCL writes its banner ("NCCL version ...", when NCCL_DEBUG is set) to stdout by default;
         # stdout carries the driver's parsed lines (v6_test.c:64,86) / bench.py's JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (NCCL_DEBUG_FILE is ignored at level VERSION, so that level is dropped; other levels log to a file)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
+        elif os.environ.get("NCCL_DEBUG"):
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         import torch.distributed as dist
         if not dist.is_initialized():
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
