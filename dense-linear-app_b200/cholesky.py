@@ -121,10 +121,11 @@ class TiledCholesky:
                 ptr[i] = pbase + slot[i] * tb
         return ptr
 
-    def _update_tasks(self, k: int, c_base: int, a_ptr: np.ndarray) -> tuple[np.ndarray, int]:
+    def _update_tasks(self, k: int, c_base: int, a_ptr: np.ndarray) -> tuple[np.ndarray, int, int]:
         """Task records (C, A, B, flags) of the trailing update of step k for the local tiles
         (i,j), i>=j>k: C_ij -= A_ik A_jk^T, lower only when i == j (client loop v1:307-329).
-        Column k+1 first (part a); returns (tasks[n,4], n_part_a)."""
+        Column k+1 first (part a), and inside it the diagonal tile (k+1,k+1) first when owned;
+        returns (tasks[n,4], n_diag in {0,1}, n_part_a)."""
         lay, tb, P = self.lay, self.tile_bytes, self.grid.P
         cols = [j for j in lay.cols if j > k]
         parts_a, parts_b = [], []
@@ -140,6 +141,7 @@ class TiledCholesky:
             rec[:, 3] = (rows == j).astype(np.int64)
             (parts_a if j == k + 1 else parts_b).append((rows, rec))
         na = sum(r.shape[0] for _, r in parts_a)
+        nd = 1 if (parts_a and int(parts_a[0][0][0]) == k + 1) else 0
         if parts_b:
             rows_b = np.concatenate([r for r, _ in parts_b])
             rec_b = np.concatenate([r for _, r in parts_b])
@@ -149,22 +151,22 @@ class TiledCholesky:
         else:
             recs = [r for _, r in parts_a]
         if not recs:
-            return np.zeros((0, 4), dtype=np.int64), 0
-        return np.concatenate(recs), na
+            return np.zeros((0, 4), dtype=np.int64), 0, 0
+        return np.concatenate(recs), nd, na
 
     def _build_plan(self) -> None:
         nt, tb = self.nt, self.tile_bytes
         base = self.A.buf.data_ptr()
-        all_tasks, self.step_tasks = [], []   # step_tasks[k] = (offset, n_a, n_total)
+        all_tasks, self.step_tasks = [], []   # step_tasks[k] = (offset, n_diag, n_a, n_total)
         trsm_ptrs, self.step_trsm = [], []    # step_trsm[k] = (offset, count) of owned panel tiles
         off = toff = 0
         self.a_ptrs = []
         for k in range(nt):
             a_ptr = self._panel_ptrs(k, base)
             self.a_ptrs.append(a_ptr)
-            rec, na = self._update_tasks(k, base, a_ptr)
+            rec, nd, na = self._update_tasks(k, base, a_ptr)
             all_tasks.append(rec)
-            self.step_tasks.append((off, na, rec.shape[0]))
+            self.step_tasks.append((off, nd, na, rec.shape[0]))
             off += rec.shape[0]
             if (k % self.grid.Q) == self.lay.q:
                 rows = np.asarray(self.lay.rows_in_col(k, k), dtype=np.int64)
@@ -208,27 +210,38 @@ class TiledCholesky:
     def _stream_ptr(self, s) -> int:
         return s.cuda_stream if s is not None else 0
 
-    def _panel_step(self, k: int, factor: bool = True) -> None:
-        """Everything of step k that happens before the trailing update: POTRF, TRSM, broadcasts.
-        Runs on the panel stream.  With factor=False only the broadcasts run (residual mode)."""
+    def _panel_potrf(self, k: int, factor: bool = True) -> None:
+        """First half of panel step k (panel stream): POTRF of tile (k,k) on its owner and the
+        broadcast of L_kk + its inverted diagonal blocks down the owner's process column.  Needs
+        only tile (k,k) up to date, so it starts as soon as the diagonal SYRK of step k-1 is done."""
+        if not factor:
+            return
         g, lay, nt = self.grid, self.lay, self.nt
         st = self._stream_ptr(self.s_panel)
         kq, kp = k % g.Q, k % g.P
         in_col = kq == lay.q
         is_diag = in_col and kp == lay.p
+        if is_diag:
+            self._k_potrf(self.A.tile_ptr(k, k), k * self.b, st)
+        self._l_ptr = self.A.tile_ptr(k, k) if is_diag else 0
+        if g.P > 1 and in_col and k + 1 < nt:
+            cg = self._column_group(kq)
+            ltile = self.A.tile(k, k) if is_diag else self.diag
+            self._bcast(ltile, kp, cg)
+            self._bcast(self.work, kp, cg)
+            self._l_ptr = ltile.data_ptr()
+
+    def _panel_rest(self, k: int, factor: bool = True) -> None:
+        """Second half of panel step k: TRSM of the owned panel tiles (needs column k up to date)
+        and the broadcast of the factored panel to every rank.  With factor=False only the
+        broadcasts run (residual mode)."""
+        g, lay, nt = self.grid, self.lay, self.nt
+        st = self._stream_ptr(self.s_panel)
+        kq = k % g.Q
         if factor:
-            if is_diag:
-                self._k_potrf(self.A.tile_ptr(k, k), k * self.b, st)
-            l_ptr = self.A.tile_ptr(k, k) if is_diag else 0
-            if g.P > 1 and in_col and k + 1 < nt:
-                cg = self._column_group(kq)
-                ltile = self.A.tile(k, k) if is_diag else self.diag
-                self._bcast(ltile, kp, cg)
-                self._bcast(self.work, kp, cg)
-                l_ptr = ltile.data_ptr()
             toff, cnt = self.step_trsm[k]
             if cnt:
-                self._k_trsm_panel(l_ptr, self.d_trsm_ptrs.data_ptr() + toff * 8, cnt, st)
+                self._k_trsm_panel(self._l_ptr, self.d_trsm_ptrs.data_ptr() + toff * 8, cnt, st)
         if self.world > 1 and k + 1 < nt:
             _, groups = panel_slots(nt, g.P, k)
             for p, first, cnt in groups:
@@ -249,55 +262,68 @@ class TiledCholesky:
             cur = torch.cuda.current_stream(self.dev)
             self.s_update.wait_stream(cur)
             self.s_panel.wait_stream(cur)
-        ev_col = None      # column k ready for its panel step
+        ev_diag = None     # tile (k,k) has all its updates      -> POTRF(k) may start
+        ev_col = None      # column k has all its updates        -> TRSM(k) may start
         ev_upd = [None, None]  # update k finished reading panel slot k%2
         for k in range(nt):
             # ---- panel k
             if cuda:
                 with torch.cuda.stream(self.s_panel):
-                    if ev_col is not None:
-                        self.s_panel.wait_event(ev_col)
                     if ev_upd[k % 2] is not None:
                         self.s_panel.wait_event(ev_upd[k % 2])
-                    self._panel_step(k, factor)
+                    if ev_diag is not None:
+                        self.s_panel.wait_event(ev_diag)
+                    self._panel_potrf(k, factor)
+                    if ev_col is not None:
+                        self.s_panel.wait_event(ev_col)
+                    self._panel_rest(k, factor)
                     ev_panel = torch.cuda.Event()
                     ev_panel.record(self.s_panel)
                 self.s_update.wait_event(ev_panel)
                 if post_panel is not None:
                     post_panel(k, ev_panel)
             else:
-                self._panel_step(k, factor)
+                self._panel_potrf(k, factor)
+                self._panel_rest(k, factor)
             # ---- trailing update k
             st = self._stream_ptr(self.s_update)
             if pre_update is not None:
                 pre_update(k, st)
-            off, na, ntot = self.step_tasks[k]
-            split = na if (self.lookahead and 0 < na < ntot) else 0
+            off, nd, na, ntot = self.step_tasks[k]
             base = update_tasks_ptr + off * 32
             if not cuda:
                 if ntot:
                     self._k_update(base, ntot, st)
                 continue
             with torch.cuda.stream(self.s_update):
-                if split:
-                    # part a: column k+1, so its panel step can start while part b runs
-                    self._k_update(base, split, st)
-                    ev_col = torch.cuda.Event()
-                    ev_col.record(self.s_update)
-                    self._k_update(base + split * 32, ntot - split, st)
-                    ev_upd[k % 2] = torch.cuda.Event()
-                    ev_upd[k % 2].record(self.s_update)
-                else:
+                if not self.lookahead:
                     if ntot:
                         self._k_update(base, ntot, st)
-                    ev_upd[k % 2] = torch.cuda.Event()
-                    ev_upd[k % 2].record(self.s_update)
-                    # a rank that owns nothing in column k+1 only receives panel k+1: it may
-                    # join that broadcast as soon as the receive slot is free (ev_upd of k-1)
-                    ev_col = None if (self.lookahead and na == 0) else ev_upd[k % 2]
+                    ev_diag = ev_col = ev_upd[k % 2] = self._record()
+                    continue
+                # lookahead: (1) the diagonal tile of column k+1 so POTRF(k+1) can start, (2) the rest
+                # of column k+1 so TRSM(k+1) can start, (3) everything else, overlapped with panel k+1.
+                # A rank that owns nothing of a stage has nothing to wait for: it only receives, and may
+                # join the broadcasts as soon as its receive slot is free (ev_upd of step k-1).
+                ev_diag = ev_col = None
+                if nd:
+                    self._k_update(base, nd, st)
+                    ev_diag = self._record()
+                if na > nd:
+                    self._k_update(base + nd * 32, na - nd, st)
+                if na:
+                    ev_col = self._record()
+                if ntot > na:
+                    self._k_update(base + na * 32, ntot - na, st)
+                ev_upd[k % 2] = self._record()
         if cuda:
             cur.wait_stream(self.s_update)
             cur.wait_stream(self.s_panel)
+
+    def _record(self):
+        ev = torch.cuda.Event()
+        ev.record(self.s_update)
+        return ev
 
     def factor(self) -> None:
         """Enqueue the whole factorization (asynchronous on CUDA).  A <- L (lower tiles)."""
