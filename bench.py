@@ -261,6 +261,13 @@ def main_ours(a) -> int:
         return 0
     tf = flops * a.steps / elapsed / 1e12
     achieved = upd_flops / upd_s / 1e12 if upd_s > 0 else None
+    traffic, traffic_note = None, None
+    ncu_json = os.path.join(ROOT, "profiles", "update_kernel_ncu.json")   # one `ncu --set full` capture, see profiles/
+    if os.path.exists(ncu_json):
+        with open(ncu_json) as f:
+            cap = json.load(f)
+        traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        traffic_note = cap["note"]
     line = {"metric": METRIC, "value": tf, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": elapsed / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, g.P, g.Q),
@@ -273,7 +280,7 @@ def main_ours(a) -> int:
                          "peak_source": "measured live: chol_fp64_peak (DMMA m8n8k4 chains, all SMs, burst); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "launches_timed": len(upd), "share_of_step": upd_s / elapsed if elapsed else None,
-                         "traffic": None}}
+                         "traffic": traffic, "traffic_note": traffic_note}}
     if not a.no_cpu_baseline and world == 1:
         try:
             cores = host_cores()

@@ -46,11 +46,12 @@ def init(ncpu: int = 0, ngpu: int | None = None) -> tuple[int, int]:
             del os.environ["NCCL_DEBUG"]
         elif os.environ.get("NCCL_DEBUG"):
             os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
-        # The panel broadcasts are tiny next to NVLink but a receiving rank joins them
-        # early and its NCCL kernel then spins on one SM per channel until the owner has factored
-        # the panel: cap the channels so the trailing update keeps its SMs (CHOL_NCCL_CHANNELS=0
-        # leaves NCCL's default; an explicit NCCL_MAX_NCHANNELS wins).
-        nch = os.environ.get("CHOL_NCCL_CHANNELS", "4")
+        # A receiving rank joins the panel broadcast early and its NCCL kernel then spins on one SM
+        # per channel until the owner has factored the panel.  CHOL_NCCL_CHANNELS=n caps the
+        # channels (measured on 8 B200: n=4 lifts the update kernel from 28.4 to 31.9 TFLOP/s but
+        # slows the broadcasts so much that the whole run drops from 204 to 183 TFLOP/s), so the
+        # default (0) leaves NCCL's own choice; an explicit NCCL_MAX_NCHANNELS wins.
+        nch = os.environ.get("CHOL_NCCL_CHANNELS", "0")
         if nch != "0":
             os.environ.setdefault("NCCL_MAX_NCHANNELS", nch)
         import torch.distributed as dist
