@@ -94,8 +94,8 @@ int chol_trsm_tile(int b, const double* L, int ldl, double* A, int lda, double* 
 
 /* Panel form: the same solve applied to `ntiles` tiles (device array of tile pointers)
  * in one launch sequence, re-using the diagonal-block inverses left in `potrf_work` by
- * chol_potrf_tile.  `d_task_scratch` >= ntiles*sizeof(chol_task_t)*2 bytes of device
- * scratch.  Replaces the TRSM loop of one wave (C1:295-303). */
+ * chol_potrf_tile.  `d_task_scratch` is reserved (the kernels address the tiles straight from
+ * the pointer list; may be NULL).  Replaces the TRSM loop of one wave (C1:295-303). */
 int chol_trsm_tiles(int b, const double* L, int ldl, const double* potrf_work,
                     double* const* d_tiles, int ntiles, int lda, void* d_task_scratch,
                     void* stream);

@@ -1,0 +1,28 @@
+"""bench.py's reference arm runs on host cores only, so its JSON contract is checked here (no GPU)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                         "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert pr.returncode == 0, pr.stderr[-2000:]
+    lines = [l for l in pr.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fp64_cholesky_tflops" and d["unit"] == "TFLOP/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["config"]["N"] == 65536 and d["config"]["tile"] == 1024
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert pr.returncode == 0 and pr.stdout.strip() == ""

@@ -1,0 +1,83 @@
+"""Invariants of the factorization plan (per-step task lists and panel pointer lists) on CPU tensors,
+for several grids: the plan is the DAG the GPU executes, so it is checked against dag.build_dag."""
+import numpy as np
+import pytest
+import torch
+
+from dense_linear_app_b200 import dag
+from dense_linear_app_b200.cholesky import TiledCholesky
+from dense_linear_app_b200.grid import ProcessGrid
+from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+
+
+class PlanOnly(TiledCholesky):
+    """Builds the plan without touching CUDA or torch.distributed."""
+
+    def __init__(self, A):
+        self.A, self.nt, self.b = A, A.nt, A.b
+        self.grid, self.rank, self.lay = A.grid, A.rank, A.layout
+        self.dev, self.cuda, self.world = A.device, False, A.grid.size
+        self.group, self.lookahead = None, True
+        self.tile_bytes = self.b * self.b * 8
+        self.panel = torch.empty((2, max(self.nt - 1, 1), self.b, self.b), dtype=torch.float64) if self.world > 1 else None
+        self._build_plan()
+
+
+@pytest.mark.parametrize("P,Q,N,b", [(1, 1, 80, 16), (1, 2, 96, 16), (2, 2, 112, 16), (2, 4, 176, 16), (2, 4, 100, 16)])
+def test_plan_is_the_reference_dag(P, Q, N, b):
+    g = ProcessGrid(P, Q)
+    desc = TileDesc(b, b, b * b, N, N, 0, 0, N, N, P, Q)
+    nt = (N + b - 1) // b
+    want = {}
+    for t in dag.build_dag(N, b):
+        if t.op in ("SYRK", "GEMM"):
+            want.setdefault(t.k, set()).add(t.out)
+    seen = {k: set() for k in range(nt)}
+    trsm_seen = {k: set() for k in range(nt)}
+    for rank in range(g.size):
+        M = TileMatrix(desc, rank, "cpu")
+        pl = PlanOnly(M)
+        base, tb = M.buf.data_ptr(), M.tile_bytes
+        ptr2tile = {base + M.layout.index(i, j) * tb: (i, j) for i, j in M.layout.tiles()}
+        lo, hi = base, base + M.buf.numel() * 8
+        plo = pl.panel.data_ptr() if pl.panel is not None else 0
+        phi = plo + pl.panel.numel() * 8 if pl.panel is not None else 0
+        for k in range(nt):
+            off, nd, na, ntot = pl.step_tasks[k]
+            rec = pl.tasks_host[off:off + ntot]
+            assert 0 <= nd <= 1 and nd <= na <= ntot
+            for n_, (c, a, bb, flag) in enumerate(rec.tolist()):
+                i, j = ptr2tile[c]                       # C is always an owned tile
+                assert i >= j > k and (flag == 1) == (i == j)
+                assert (i, j) not in seen[k]
+                seen[k].add((i, j))
+                assert (n_ < na) == (j == k + 1)          # part a = column k+1, first
+                if n_ < nd:
+                    assert (i, j) == (k + 1, k + 1)       # diagonal tile leads part a
+                for p_, row in ((a, i), (bb, j)):         # operands: tile (row, k), local or in the receive slot
+                    if lo <= p_ < hi:
+                        assert ptr2tile[p_] == (row, k)
+                    else:
+                        assert plo <= p_ < phi and (p_ - plo) % tb == 0
+                        assert (p_ - plo) // (pl.panel.stride(0) * 8) == k % 2
+            toff, cnt = pl.step_trsm[k]
+            for p_ in pl.d_trsm_ptrs[toff:toff + cnt].tolist():
+                i, j = ptr2tile[p_]
+                assert j == k and i > k
+                trsm_seen[k].add(i)
+    for k in range(nt):
+        assert seen[k] == want.get(k, set()), k           # every update of wave k exactly once over all ranks
+        assert trsm_seen[k] == set(range(k + 1, nt))
+
+
+def test_tilematrix_roundtrip_and_identity_padding():
+    N, b = 50, 16
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((N, N))
+    A = A + A.T
+    M = TileMatrix(TileDesc.square(N, b), 0, "cpu").from_numpy(A)
+    back = M.to_numpy()
+    assert np.array_equal(np.tril(back), np.tril(A))
+    last = M.tile(3, 3).numpy().T                         # column-major view of the ragged diagonal tile
+    assert np.array_equal(last[2:, 2:], np.eye(14)) and not last[2:, :2].any()
+    assert M.clone().buf.data_ptr() != M.buf.data_ptr()
