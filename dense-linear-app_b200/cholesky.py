@@ -145,8 +145,11 @@ class TiledCholesky:
         if parts_b:
             rows_b = np.concatenate([r for r, _ in parts_b])
             rec_b = np.concatenate([r for _, r in parts_b])
-            # row-major over (i, j): consecutive tasks share the A operand (tile (i,k)) in L2
-            rec_b = rec_b[np.argsort(rows_b, kind="stable")]
+            if k > 0:
+                # row-major over (i, j): consecutive tasks share the A operand (tile (i,k)) in L2
+                rec_b = rec_b[np.argsort(rows_b, kind="stable")]
+            # step 0 stays column-major = storage order (consecutive tasks share the B operand):
+            # factor_from_host uploads the tiles in that order and releases the update group by group
             recs = [r for _, r in parts_a] + [rec_b]
         else:
             recs = [r for _, r in parts_a]
@@ -183,6 +186,29 @@ class TiledCholesky:
         max_panel = max((c for _, c in self.step_trsm), default=0)
         self.trsm_scratch = torch.empty(max(max_panel, 1) * 8, dtype=torch.int64, device=self.dev)
         self.n_update_tasks = off
+        self.step0_head, self.step0_groups = self._step0_groups()
+
+    def _step0_groups(self, ngroups: int = 8):
+        """Upload/compute pipeline of factor_from_host for step 0.  Returns (head_hi, groups): local
+        tiles [0, head_hi) are columns 0 and 1 (panel 0 and part a); every later local tile is the C
+        operand of exactly one part-b task of step 0, in the same (column-major) order, so group g =
+        (task0, task1, tile_lo, tile_hi) can start as soon as tiles [0, tile_hi) are on the device."""
+        lay = self.lay
+        cols = [j for j in lay.cols if j >= 2]
+        head_hi = lay.col_start[cols[0]] if cols else lay.ntiles
+        groups = []
+        total = lay.ntiles - head_hi
+        if total > 0:
+            target = max(1, -(-total // ngroups))
+            t0, lo = 0, head_hi
+            for n, j in enumerate(cols):
+                nxt = lay.col_start[cols[n + 1]] if n + 1 < len(cols) else lay.ntiles
+                if nxt - lo >= target or n + 1 == len(cols):
+                    if nxt > lo:
+                        groups.append((t0, t0 + (nxt - lo), lo, nxt))
+                    t0 += nxt - lo
+                    lo = nxt
+        return head_hi, groups
 
     def _make_column_groups(self) -> None:
         import torch.distributed as dist
@@ -255,7 +281,7 @@ class TiledCholesky:
                     buf = self.panel[k % 2, first:first + cnt]
                 self._bcast(buf, root, self.group)
 
-    def _run(self, update_tasks_ptr: int, factor: bool, pre_update=None, post_panel=None) -> None:
+    def _run(self, update_tasks_ptr: int, factor: bool, pre_update=None, post_panel=None, step0_gates=None) -> None:
         nt = self.nt
         cuda = self.cuda
         if cuda:
@@ -273,6 +299,8 @@ class TiledCholesky:
                         self.s_panel.wait_event(ev_upd[k % 2])
                     if ev_diag is not None:
                         self.s_panel.wait_event(ev_diag)
+                    if k == 0 and step0_gates:
+                        self.s_panel.wait_event(step0_gates[0])      # columns 0 and 1 are on the device
                     self._panel_potrf(k, factor)
                     if ev_col is not None:
                         self.s_panel.wait_event(ev_col)
@@ -296,6 +324,10 @@ class TiledCholesky:
                     self._k_update(base, ntot, st)
                 continue
             with torch.cuda.stream(self.s_update):
+                gated = k == 0 and bool(step0_gates)
+                if gated:
+                    for ev in (step0_gates if not self.lookahead else step0_gates[:1]):
+                        self.s_update.wait_event(ev)
                 if not self.lookahead:
                     if ntot:
                         self._k_update(base, ntot, st)
@@ -313,7 +345,12 @@ class TiledCholesky:
                     self._k_update(base + nd * 32, na - nd, st)
                 if na:
                     ev_col = self._record()
-                if ntot > na:
+                if gated:
+                    # host-resident input: release part b group by group behind the upload
+                    for g, (t0, t1, _, _) in enumerate(self.step0_groups):
+                        self.s_update.wait_event(step0_gates[1 + g])
+                        self._k_update(base + (na + t0) * 32, t1 - t0, st)
+                elif ntot > na:
                     self._k_update(base + na * 32, ntot - na, st)
                 ev_upd[k % 2] = self._record()
         if cuda:
@@ -344,8 +381,20 @@ class TiledCholesky:
         cur = torch.cuda.current_stream(self.dev)
         if getattr(self, "s_copy", None) is None:
             self.s_copy = torch.cuda.Stream(self.dev)
-        self.A.buf.copy_(host_in, non_blocking=True)
+        if getattr(self, "s_h2d", None) is None:
+            self.s_h2d = torch.cuda.Stream(self.dev)
         self.d_info.zero_()
+        # upload in storage (column-major) order on its own stream: columns 0-1 first, then the
+        # groups of step 0's part b; each group of the update waits only for its own tiles
+        gates = []
+        self.s_h2d.wait_stream(cur)
+        with torch.cuda.stream(self.s_h2d):
+            for lo, hi in [(0, self.step0_head)] + [(g[2], g[3]) for g in self.step0_groups]:
+                if hi > lo:
+                    self.A.buf[lo:hi].copy_(host_in[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.s_h2d)
+                gates.append(ev)
         lay, nt = self.lay, self.nt
         bounds = {j: (lay.col_start[j], lay.col_start[lay.cols[n + 1]] if n + 1 < len(lay.cols) else lay.ntiles)
                   for n, j in enumerate(lay.cols)}
@@ -357,8 +406,9 @@ class TiledCholesky:
                 with torch.cuda.stream(self.s_copy):
                     host_out[lo:hi].copy_(self.A.buf[lo:hi], non_blocking=True)
 
-        self._run(self.d_tasks.data_ptr(), factor=True, post_panel=post_panel)
+        self._run(self.d_tasks.data_ptr(), factor=True, post_panel=post_panel, step0_gates=gates)
         cur.wait_stream(self.s_copy)
+        cur.wait_stream(self.s_h2d)
 
     def info(self) -> int:
         """LAPACK info of the last factor(): 0, or the 1-based global index of the first

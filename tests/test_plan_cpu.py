@@ -60,6 +60,17 @@ def test_plan_is_the_reference_dag(P, Q, N, b):
                     else:
                         assert plo <= p_ < phi and (p_ - plo) % tb == 0
                         assert (p_ - plo) // (pl.panel.stride(0) * 8) == k % 2
+            if k == 0:
+                # step 0, part b: one task per local tile of columns >= 2, in storage order; the upload
+                # groups of factor_from_host tile that range without gaps
+                head, groups = pl.step0_head, pl.step0_groups
+                assert [ptr2tile[c] for c in rec[na:, 0].tolist()] == [t for t in M.layout.tiles() if t[1] >= 2]
+                assert rec[na:, 0].tolist() == [base + (head + n_) * tb for n_ in range(ntot - na)]
+                t_next, lo_next = 0, head
+                for t0, t1, tlo, thi in groups:
+                    assert (t0, tlo) == (t_next, lo_next) and t1 - t0 == thi - tlo > 0
+                    t_next, lo_next = t1, thi
+                assert t_next == ntot - na and lo_next == M.layout.ntiles
             toff, cnt = pl.step_trsm[k]
             for p_ in pl.d_trsm_ptrs[toff:toff + cnt].tolist():
                 i, j = ptr2tile[p_]
