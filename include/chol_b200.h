@@ -127,8 +127,9 @@ int chol_plgsy_tile(double bump, int mb, int nb, double* A, int lda, long long b
                     long long row0, long long col0, long long N, unsigned long long seed,
                     void* stream);
 
-/* sum of squares of a tile -> d_out[0] (mode 0: all m x n entries; mode 1: lower triangle
- * counted as a symmetric matrix, i.e. strict lower twice + diagonal once). */
+/* per-column sums of squares of a tile -> d_out[n] (mode 0: all m rows; mode 1: lower triangle
+ * counted as a symmetric matrix, i.e. strict lower twice + diagonal once, rows above the diagonal
+ * ignored).  Building block of the Frobenius norm of the residual (V6:72-86). */
 int chol_tile_sumsq(int m, int n, const double* A, int lda, int mode, double* d_out,
                     void* stream);
 /* per-row and per-column sums of |a_ij| of a tile (mode as above: mode 1 reads only the

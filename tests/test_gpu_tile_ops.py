@@ -197,3 +197,31 @@ def test_trsm_panel_form_matches_single_tile_op(cuda_lib, oracle, b, m):
         got = host_cm(panel[i])
         assert np.abs(got - ref).max() <= TOL * max(1.0, np.abs(ref).max()) * max(1, b / 64)
     assert torch.equal(panel, single), "panel form and single-tile form must agree bit for bit"
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 3), (64, 64), (200, 130), (512, 512)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_norm_building_blocks(cuda_lib, m, n, mode):
+    """chol_tile_sumsq / chol_tile_abs_sums (dlange building blocks, v6_test.c:72,84) against numpy."""
+    from dense_linear_app_b200 import _lib
+    if mode == 1 and m != n:
+        pytest.skip("lower-triangle mode is for square (diagonal) tiles")
+    rng = np.random.default_rng(m * 1000 + n)
+    A = np.asfortranarray(rng.uniform(-1, 1, (m, n)))
+    dA = dev_cm(A)
+    st = torch.cuda.current_stream().cuda_stream
+    ssq = torch.zeros(n, dtype=torch.float64, device="cuda")
+    rows = torch.zeros(m, dtype=torch.float64, device="cuda")
+    cols = torch.zeros(n, dtype=torch.float64, device="cuda")
+    _lib.call("chol_tile_sumsq", m, n, dA.data_ptr(), m, mode, ssq.data_ptr(), st)
+    _lib.call("chol_tile_abs_sums", m, n, dA.data_ptr(), m, mode, rows.data_ptr(), cols.data_ptr(), st)
+    if mode == 0:
+        want_ssq, want_rows, want_cols = (A * A).sum(0), np.abs(A).sum(1), np.abs(A).sum(0)
+    else:
+        L = np.tril(A)
+        W = np.tril(np.full((n, n), 2.0), -1) + np.eye(n)
+        want_ssq, want_rows, want_cols = (W * L * L).sum(0), np.abs(L).sum(1), np.abs(L).sum(0)
+    tol = 1e-13 * max(m, n)
+    assert np.abs(ssq.cpu().numpy() - want_ssq).max() <= tol
+    assert np.abs(rows.cpu().numpy() - want_rows).max() <= tol
+    assert np.abs(cols.cpu().numpy() - want_cols).max() <= tol
