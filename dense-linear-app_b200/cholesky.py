@@ -10,10 +10,12 @@ Schedule (per rank; one rank per GPU, tiles 2D block-cyclic, see grid.py):
   * panel stream (high priority): POTRF of the diagonal tile on its owner, broadcast of L_kk and
     the inverted diagonal blocks down the owner's process column, TRSM of the panel tiles on
     their owners (one grouped launch sequence), broadcast of the factored panel to all ranks;
-  * update stream: the fused SYRK+GEMM trailing update of step k as ONE grouped launch over
-    every local tile (i,j), i>=j>k — split in two so that column k+1 is finished first
-    (part a) and the panel stream can factor panel k+1 while the rest (part b) still runs:
-    lookahead of depth 1.
+  * update stream: the fused SYRK+GEMM trailing update of step k as grouped launches over every
+    local tile (i,j), i>=j>k, in three stages: the diagonal tile (k+1,k+1) — POTRF(k+1) starts
+    right after it —, the rest of column k+1 — then TRSM(k+1) —, and everything else, which
+    overlaps panel step k+1: lookahead of depth 1;
+  * with host-resident input (factor_from_host) a third and fourth stream upload the tiles in
+    storage order underneath step 0 and copy each finished panel column back.
 Nothing synchronises with the host between steps; LAPACK ``info`` is a device int read at the end.
 """
 from __future__ import annotations
