@@ -121,6 +121,22 @@ def run_cpu_reference_once(threads: int) -> dict:
             "sample": f"oracle port: OpenBLAS dpotrf N={N}, {threads} threads, one factorization"}
 
 
+def run_cpu_tiled_single_worker() -> dict:
+    """BASELINE configs[0]: N=4096, tile 512, the reference-style tiled Cholesky on ONE CPU worker
+    (tile DAG in the client's order, OpenBLAS tile kernels with 1 BLAS thread as benchmark.c:173-175
+    forces) — the oracle's port of that path, timed; a reported baseline only."""
+    from oracle import oracle as O
+    N, b = 4096, 512
+    A = O.plgsy(float(N), N, 42)
+    tiles = O.to_tiles(A, b)
+    t0 = time.time()
+    info = O.blas_potrf_tiled(tiles, N // b, b, threads=1)
+    dt = time.time() - t0
+    L = O.from_tiles(tiles, N // b, b)
+    return {"workload": "N=4096, tile 512, tile DAG, 1 worker, 1 BLAS thread (configs[0])", "seconds": dt,
+            "tflops": N ** 3 / 3 / dt / 1e12, "info": int(info), "backward_error": O.backward_error_blas(A, L)}
+
+
 def main_reference(a) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,11 +149,13 @@ def main_reference(a) -> int:
     runs = [run_cpu_reference_once(cores) for _ in range(a.steps)]
     tf = sum(r["N"] ** 3 / 3 for r in runs) / sum(r["seconds"] for r in runs) / 1e12
     ms = sum(r["seconds"] for r in runs) / len(runs) * 1e3
+    tiled = run_cpu_tiled_single_worker()
     line = {"impl": "reference", "metric": METRIC, "value": tf, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, g.P, g.Q),
             "cpu_baseline": {"value": tf, "unit": UNIT, "cores": cores, "kind": runs[0]["kind"],
-                             "sample": runs[0]["sample"] + f" per step, {a.steps} steps"},
+                             "sample": runs[0]["sample"] + f" per step, {a.steps} steps",
+                             "tiled_single_worker": tiled},
             "e2e": {"value": tf, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -286,7 +304,7 @@ def main_ours(a) -> int:
             cores = host_cores()
             r = run_cpu_reference_once(cores)
             line["cpu_baseline"] = {"value": r["tflops"], "unit": UNIT, "cores": cores, "kind": r["kind"],
-                                    "sample": r["sample"]}
+                                    "sample": r["sample"], "tiled_single_worker": run_cpu_tiled_single_worker()}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port",
                                     "sample": f"failed: {e}"}

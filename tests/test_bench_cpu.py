@@ -26,3 +26,22 @@ def test_reference_arm_other_ranks_exit_quietly():
     pr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert pr.returncode == 0 and pr.stdout.strip() == ""
+
+
+def test_sweep_writes_reference_csv_rows_even_when_the_driver_fails(tmp_path):
+    """benchmark.c:257-285 appends a row for every run, with -1 metrics and the child's exit code when
+    the driver fails; on this GPU-less box the driver fails loudly (no CPU path), which exercises that."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present: the driver would succeed")
+    csv = tmp_path / "results" / "bench.csv"
+    pr = subprocess.run([sys.executable, "-m", "dense_linear_app_b200.bench_sweep", "--N", "64", "--NB", "16",
+                         "--repeats", "1", "--sched", "lookahead", "--csv", str(csv)],
+                        capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert pr.returncode == 0, pr.stderr[-1500:]
+    rows = csv.read_text().splitlines()
+    assert rows[0] == "timestamp,scheduler,mapping,ncpu,ngpu,N,NB,run_idx,ms,exit_code,gflops,rel_error"
+    f = rows[1].split(",")
+    assert f[1:8] == ["lookahead", "1_b200", "0", "1", "64", "16", "0"]
+    assert int(f[9]) != 0 and float(f[10]) == -1.0 and float(f[11]) == -1.0
