@@ -79,8 +79,7 @@ class TiledCholesky:
         _lib.call("chol_potrf_tile", self.b, a_ptr, self.b, self.work.data_ptr(), self.d_info.data_ptr(), info_base, st)
 
     def _k_trsm_panel(self, l_ptr: int, tiles_ptr: int, ntiles: int, st: int) -> None:
-        _lib.call("chol_trsm_tiles", self.b, l_ptr, self.b, self.work.data_ptr(), tiles_ptr, ntiles, self.b,
-                  self.trsm_scratch.data_ptr(), st)
+        _lib.call("chol_trsm_tiles", self.b, l_ptr, self.b, self.work.data_ptr(), tiles_ptr, ntiles, self.b, None, st)
 
     def _k_update(self, tasks_ptr: int, ntasks: int, st: int) -> None:
         b = self.b
@@ -165,10 +164,8 @@ class TiledCholesky:
         all_tasks, self.step_tasks = [], []   # step_tasks[k] = (offset, n_diag, n_a, n_total)
         trsm_ptrs, self.step_trsm = [], []    # step_trsm[k] = (offset, count) of owned panel tiles
         off = toff = 0
-        self.a_ptrs = []
         for k in range(nt):
             a_ptr = self._panel_ptrs(k, base)
-            self.a_ptrs.append(a_ptr)
             rec, nd, na = self._update_tasks(k, base, a_ptr)
             all_tasks.append(rec)
             self.step_tasks.append((off, nd, na, rec.shape[0]))
@@ -185,8 +182,6 @@ class TiledCholesky:
         self.tasks_host = tasks
         self.d_tasks = torch.from_numpy(tasks).to(self.dev)
         self.d_trsm_ptrs = torch.from_numpy(tptr).to(self.dev)
-        max_panel = max((c for _, c in self.step_trsm), default=0)
-        self.trsm_scratch = torch.empty(max(max_panel, 1) * 8, dtype=torch.int64, device=self.dev)
         self.n_update_tasks = off
         self.step0_head, self.step0_groups = self._step0_groups()
 

@@ -27,14 +27,19 @@ def env_int(key: str, default: int) -> int:
 
 
 def init(ncpu: int = 0, ngpu: int | None = None) -> tuple[int, int]:
-    """Returns (rank, world).  `ncpu` is accepted for signature parity and ignored (no CPU
-    workers exist); `ngpu` defaults to env CHM_NGPU (worker_distrib.cpp:585) or WORLD_SIZE."""
+    """Returns (rank, world).  `ncpu` is accepted for signature parity and ignored (no CPU workers
+    exist).  The number of GPUs is the number of launched ranks (WORLD_SIZE); `ngpu` — or env
+    CHM_NGPU, the worker's knob (worker_distrib.cpp:585) — is only checked against it."""
     if _state["inited"]:
         return _state["rank"], _state["world"]
     if not torch.cuda.is_available():
         raise RuntimeError("dense-linear-app_b200 needs a CUDA device (B200): there is no CPU path")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    want = ngpu if ngpu else env_int("CHM_NGPU", 0)
+    if want and want != world and rank == 0:
+        import sys
+        sys.stderr.write(f"[setup] ngpu={want} requested but {world} rank(s) launched: using {world} GPU(s)\n")
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     _lib.call("chol_init", local)

@@ -68,6 +68,7 @@ def _worker(rank, world, port, P, Q, N, b, lookahead, bad):
     (1, 2, 100, 16, False),     # ragged edge
     (2, 2, 112, 16, True),
     (2, 1, 80, 16, True),
+    (2, 4, 160, 16, True),      # the 8-GPU grid shape
 ])
 def test_block_cyclic_schedule_gloo(P, Q, N, b, lookahead):
     world = P * Q
