@@ -188,3 +188,42 @@ def test_sweep_contract():
     assert bench_sweep.driver_argv(0, 1, 1000, 128, 1, 1, 42) == ["0", "1", "1000", "128", "128", "128", "16384", "1000",
                                                                   "1000", "0", "0", "1000", "1000", "1", "1", "42"]
     assert bench_sweep.NS == (1000, 5000, 8000, 12000, 16000) and bench_sweep.NBS[0] == 128 and bench_sweep.REPEATS == 8
+
+
+def test_v3_named_argument_cli_checks():
+    """v3_script_cholesky_x_arg_gpt.c:131-199: all 20 options required, strict geometry, same messages."""
+    import io
+    from dense_linear_app_b200 import v3_cli
+    good = ("--N 3000 --NB 256 --ncpu 4 --ngpu 1 --mat none --dtyp d --mb 256 --nb 256 --bsiz 65536 --lm 3000 "
+            "--ln 3000 --i 0 --j 0 --m 3000 --n 3000 --p 1 --q 1 --bump 3000 --uplo L --seed 51").split()
+
+    def run(args):
+        err = io.StringIO()
+        code, a = v3_cli.parse(["v3"] + args, err)
+        return code, a, err.getvalue()
+
+    code, a, _ = run(good)
+    assert code is None and a["N"] == 3000 and a["bsiz"] == 65536 and a["bump"] == 3000.0 and a["seed"] == 51
+    assert a["dtyp"] == "d" and a["uplo"] == "L" and not a["mat_user"]
+    code, a, _ = run(["--N=3000"] + good[2:])
+    assert code is None and a["N"] == 3000                         # --name=value form
+    assert run(good[:-2])[0] == 1 and "all options are required" in run(good[:-2])[2]
+    assert run(["--help"])[0] == 0
+    assert run(["--bogus", "1"] + good)[0] == 1
+
+    def with_(name, val):
+        out = list(good)
+        out[out.index("--" + name) + 1] = val
+        return out
+
+    assert "invalid --dtyp q" in run(with_("dtyp", "q"))[2]
+    assert "invalid --uplo X" in run(with_("uplo", "X"))[2]
+    assert "must be >0" in run(with_("p", "0"))[2]
+    assert "--bsiz < mb*nb (bsiz=100 mb=256 nb=256)" in run(with_("bsiz", "100"))[2]
+    assert "invalid offsets i=3000 j=0 (lm=3000 ln=3000)" in run(with_("i", "3000"))[2]
+    assert "submatrix (i=8,m=3000) outside lm=3000" in run(with_("i", "8"))[2]
+    code, a, msg = run(with_("bump", "0"))
+    assert code is None and "bump==0" in msg
+    assert run(with_("uplo", "u"))[1]["uplo"] == "U" and run(with_("dtyp", "2"))[1]["dtyp"] == "z"
+    # unsupported-but-valid choices are refused before any CUDA work
+    assert v3_cli.main(["v3"] + with_("uplo", "U")) == 1 and v3_cli.main(["v3"] + with_("dtyp", "s")) == 1
