@@ -20,6 +20,8 @@ Nothing synchronises with the host between steps; LAPACK ``info`` is a device in
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -55,8 +57,19 @@ class TiledCholesky:
         # receive buffers (only with more than one rank): panel column k, two slots for lookahead
         self.panel = None
         self.diag = None
+        # How the factored panel reaches the other ranks: "nccl" = one ncclBroadcast per owner row
+        # (measured, default); "symm" = EXPERIMENTAL peer copies into symmetric receive buffers on
+        # the copy engines + stream-ordered flags, no kernel resident on the receivers (DESIGN.md
+        # section 8; written at the end of round 1 without GPU time left, not yet run on hardware).
+        self.transport = os.environ.get("CHOL_PANEL_TRANSPORT", "nccl") if (self.world > 1 and self.cuda) else "nccl"
+        if self.transport not in ("nccl", "symm"):
+            raise ValueError("CHOL_PANEL_TRANSPORT must be 'nccl' or 'symm'")
+        self.nslots = 2
         if self.world > 1:
-            self.panel = torch.empty((2, max(nt - 1, 1), b, b), **f64)
+            if self.transport == "symm":
+                self._setup_symm_panel()
+            else:
+                self.panel = torch.empty((2, max(nt - 1, 1), b, b), **f64)
             self.diag = torch.empty((b, b), **f64)
         self._col_groups = None
         if self.world > 1 and self.grid.P > 1:
@@ -113,7 +126,7 @@ class TiledCholesky:
             ptr[rows] = base_local + (self.lay.col_start[k] + rows - k) * tb
             return ptr
         slot, _ = panel_slots(nt, self.grid.P, k)
-        pbase = self.panel.data_ptr() + (k % 2) * self.panel.stride(0) * 8
+        pbase = self.panel.data_ptr() + (k % self.nslots) * self.panel.stride(0) * 8
         mine_col = (k % self.grid.Q) == self.lay.q
         for i in range(k + 1, nt):
             if mine_col and i % self.grid.P == self.lay.p:
@@ -267,6 +280,9 @@ class TiledCholesky:
                 self._k_trsm_panel(self._l_ptr, self.d_trsm_ptrs.data_ptr() + toff * 8, cnt, st)
         if self.world > 1 and k + 1 < nt:
             _, groups = panel_slots(nt, g.P, k)
+            if self.transport == "symm":
+                self._send_panel_symm(k, groups)
+                return
             for p, first, cnt in groups:
                 if cnt == 0:
                     continue
@@ -275,8 +291,48 @@ class TiledCholesky:
                     s0 = lay.index(lay.rows_in_col(k, k)[0], k)
                     buf = self.A.buf[s0:s0 + cnt]
                 else:
-                    buf = self.panel[k % 2, first:first + cnt]
+                    buf = self.panel[k % self.nslots, first:first + cnt]
                 self._bcast(buf, root, self.group)
+
+    # ---- experimental copy-engine transport (CHOL_PANEL_TRANSPORT=symm) --------------------------
+    def _setup_symm_panel(self) -> None:
+        """Symmetric receive buffers: every rank maps every peer's panel buffer.  Q+P+2 slots: a
+        rank owns a panel at least every Q steps and can only produce panel j after finishing its
+        update j-2, so nobody runs more than Q+1 (+P near the ragged end) steps ahead of a reader."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        nt, b = self.nt, self.b
+        self.nslots = max(2, min(max(nt - 1, 1), self.grid.Q + self.grid.P + 2))
+        self.panel = symm_mem.empty((self.nslots, max(nt - 1, 1), b, b), dtype=torch.float64, device=self.dev)
+        self._symm = symm_mem.rendezvous(self.panel, self.group if self.group is not None else dist.group.WORLD)
+        self._peer_panel = [self._symm.get_buffer(r, tuple(self.panel.shape), torch.float64) if r != self.rank else None
+                            for r in range(self.world)]
+        self.s_send = torch.cuda.Stream(self.dev)
+
+    def _send_panel_symm(self, k: int, groups) -> None:
+        """Owner: after its TRSM, one peer copy per rank (copy engines over NVLink) on the send
+        stream, then a flag per rank.  Receiver: wait for the flag of each owner on the panel
+        stream.  Must be called with the panel stream current."""
+        g, lay = self.grid, self.lay
+        kq, slot = k % g.Q, k % self.nslots
+        for p, first, cnt in groups:
+            if cnt and g.rank_of(p, kq) == self.rank:
+                s0 = lay.index(lay.rows_in_col(k, k)[0], k)
+                src = self.A.buf[s0:s0 + cnt]
+                done = torch.cuda.Event()
+                done.record(self.s_panel)
+                self.s_send.wait_event(done)
+                with torch.cuda.stream(self.s_send):
+                    for r in range(self.world):
+                        if r != self.rank:
+                            self._peer_panel[r][slot, first:first + cnt].copy_(src, non_blocking=True)
+                    for r in range(self.world):
+                        if r != self.rank:
+                            self._symm.put_signal(r, 0)
+        for p, first, cnt in groups:
+            root = g.rank_of(p, kq)
+            if cnt and root != self.rank:
+                self._symm.wait_signal(root, 0)
 
     def _run(self, update_tasks_ptr: int, factor: bool, pre_update=None, post_panel=None, step0_gates=None) -> None:
         nt = self.nt
@@ -287,13 +343,14 @@ class TiledCholesky:
             self.s_panel.wait_stream(cur)
         ev_diag = None     # tile (k,k) has all its updates      -> POTRF(k) may start
         ev_col = None      # column k has all its updates        -> TRSM(k) may start
-        ev_upd = [None, None]  # update k finished reading panel slot k%2
+        ns = self.nslots
+        ev_upd = [None] * ns   # update k finished reading panel slot k % nslots
         for k in range(nt):
             # ---- panel k
             if cuda:
                 with torch.cuda.stream(self.s_panel):
-                    if ev_upd[k % 2] is not None:
-                        self.s_panel.wait_event(ev_upd[k % 2])
+                    if ev_upd[k % ns] is not None:
+                        self.s_panel.wait_event(ev_upd[k % ns])
                     if ev_diag is not None:
                         self.s_panel.wait_event(ev_diag)
                     if k == 0 and step0_gates:
@@ -328,7 +385,7 @@ class TiledCholesky:
                 if not self.lookahead:
                     if ntot:
                         self._k_update(base, ntot, st)
-                    ev_diag = ev_col = ev_upd[k % 2] = self._record()
+                    ev_diag = ev_col = ev_upd[k % ns] = self._record()
                     continue
                 # lookahead: (1) the diagonal tile of column k+1 so POTRF(k+1) can start, (2) the rest
                 # of column k+1 so TRSM(k+1) can start, (3) everything else, overlapped with panel k+1.
@@ -349,10 +406,12 @@ class TiledCholesky:
                         self._k_update(base + (na + t0) * 32, t1 - t0, st)
                 elif ntot > na:
                     self._k_update(base + na * 32, ntot - na, st)
-                ev_upd[k % 2] = self._record()
+                ev_upd[k % ns] = self._record()
         if cuda:
             cur.wait_stream(self.s_update)
             cur.wait_stream(self.s_panel)
+            if self.transport == "symm":
+                cur.wait_stream(self.s_send)
 
     def _record(self):
         ev = torch.cuda.Event()
