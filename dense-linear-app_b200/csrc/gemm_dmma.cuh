@@ -10,13 +10,17 @@
 // is the multiply step of the blocked TRSM (W2:323).
 //
 // Design (B200):
-//   * CTA tile 128x128, K sliced in slabs of 16; 8 consumer warps (2 x 4) each own a
-//     64x32 sub-tile held in registers as 32 m8n8k4 DMMA accumulators (64 doubles);
+//   * CTA tile 128 x BN, K sliced in slabs of 16; consumer warps (2 x BN/32) each own a 64x32
+//     sub-tile held in registers as 32 m8n8k4 DMMA accumulators (64 doubles);
 //   * 1 producer warp stages slabs with the TMA engine: one `cp.async.bulk` (UBLKCP) per
 //     slab column (a column of a col-major tile is contiguous), completion counted on an
-//     mbarrier (full/empty ring, 6 stages = 198 KB of the 227 KB shared memory);
-//   * slab columns are placed at a pitch of 132 doubles (128 + 4): the fragment loads are
-//     LDS.128 with lane -> (k = lane&3, rows 2*(lane>>2)..+1), which that pitch makes
+//     mbarrier (full/empty ring);
+//   * two shapes (GemmCfg below): BN=64, 4 consumer warps, 4 stages (100 KB), TWO CTAs per SM for
+//     the trailing update — one CTA's pipeline fill and C epilogue hide behind the other's main
+//     loop (ncu: DMMA pipe 85.7 -> 92.8 % active); BN=128, 8 consumer warps, 6 stages (198 KB), one
+//     CTA per SM for the in-place multiply steps of the blocked TRSM/POTRF;
+//   * slab columns are placed at a pitch of BM+4 / BN+4 doubles: the fragment loads are
+//     LDS.128 with lane -> (k = lane&3, rows 2*(lane>>2)..+1), which those pitches make
 //     bank-conflict free (each quarter warp covers all 8 16-byte bank groups);
 //   * one LDS.128 feeds two DMMAs (even/odd rows), so a k4 step is 6 LDS.128 : 32 DMMA;
 //   * C is read-modify-written straight from the accumulators: each lane owns 2x4
