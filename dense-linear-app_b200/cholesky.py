@@ -307,11 +307,12 @@ class TiledCholesky:
         self._symm = symm_mem.rendezvous(self.panel, self.group if self.group is not None else dist.group.WORLD)
         self._peer_panel = [self._symm.get_buffer(r, tuple(self.panel.shape), torch.float64) if r != self.rank else None
                             for r in range(self.world)]
-        self.s_send = torch.cuda.Stream(self.dev)
+        # one send stream per peer: the copies to different peers run on different copy engines / links
+        self.s_sends = [torch.cuda.Stream(self.dev) if r != self.rank else None for r in range(self.world)]
 
     def _send_panel_symm(self, k: int, groups) -> None:
-        """Owner: after its TRSM, one peer copy per rank (copy engines over NVLink) on the send
-        stream, then a flag per rank.  Receiver: wait for the flag of each owner on the panel
+        """Owner: after its TRSM, one peer copy per rank (copy engines over NVLink), each on that
+        peer's send stream and followed by that peer's flag.  Receiver: wait for the flag of each owner on the panel
         stream.  Must be called with the panel stream current."""
         g, lay = self.grid, self.lay
         kq, slot = k % g.Q, k % self.nslots
@@ -321,14 +322,13 @@ class TiledCholesky:
                 src = self.A.buf[s0:s0 + cnt]
                 done = torch.cuda.Event()
                 done.record(self.s_panel)
-                self.s_send.wait_event(done)
-                with torch.cuda.stream(self.s_send):
-                    for r in range(self.world):
-                        if r != self.rank:
-                            self._peer_panel[r][slot, first:first + cnt].copy_(src, non_blocking=True)
-                    for r in range(self.world):
-                        if r != self.rank:
-                            self._symm.put_signal(r, 0)
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    self.s_sends[r].wait_event(done)
+                    with torch.cuda.stream(self.s_sends[r]):
+                        self._peer_panel[r][slot, first:first + cnt].copy_(src, non_blocking=True)
+                        self._symm.put_signal(r, 0)
         for p, first, cnt in groups:
             root = g.rank_of(p, kq)
             if cnt and root != self.rank:
@@ -411,7 +411,9 @@ class TiledCholesky:
             cur.wait_stream(self.s_update)
             cur.wait_stream(self.s_panel)
             if self.transport == "symm":
-                cur.wait_stream(self.s_send)
+                for s_ in self.s_sends:
+                    if s_ is not None:
+                        cur.wait_stream(s_)
 
     def _record(self):
         ev = torch.cuda.Event()

@@ -177,7 +177,8 @@ class RankSim(TiledCholesky):
         for q in range(self.grid.Q):
             g.comm_size[("col", q)] = self.grid.P
         self._build_plan()
-        self.s_update, self.s_panel, self.s_send = SimStream(g, self.rank), SimStream(g, self.rank), SimStream(g, self.rank)
+        self.s_update, self.s_panel = SimStream(g, self.rank), SimStream(g, self.rank)
+        self.s_sends = [SimStream(g, self.rank) if r != self.rank else None for r in range(self.world)]
         self.cur = SimStream(g, self.rank)
         self._symm = SymmHandle(g, self.rank)
         self._seq = {}
