@@ -26,12 +26,27 @@ SIGNATURES = {
     "chol_syrk_tile": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "chol_gemm_tile": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "chol_potrf_batched": (c_int, [c_int, c_int, c_void_p, c_int, c_ll, c_void_p, c_void_p]),
+    "chol_peer_alloc": (c_int, [c_size_t, C.POINTER(c_void_p)]),
+    "chol_peer_free": (c_int, [c_void_p]),
+    "chol_peer_export": (c_int, [c_void_p, c_void_p]),
+    "chol_peer_open": (c_int, [c_void_p, C.POINTER(c_void_p)]),
+    "chol_peer_close": (c_int, [c_void_p]),
+    "chol_peer_send": (c_int, [c_void_p, c_int, c_void_p]),
+    "chol_flag_wait": (c_int, [c_void_p, C.c_uint32, c_void_p]),
+    "chol_flag_post": (c_int, [c_void_p, c_int, C.c_uint32, c_void_p]),
     "chol_plgsy_tile": (c_int, [c_double, c_int, c_int, c_void_p, c_int, c_ll, c_ll, c_ll, c_ll, c_ull, c_void_p]),
     "chol_tile_sumsq": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "chol_tile_abs_sums": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "chol_tile_tril": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "chol_fp64_peak": (c_int, [c_int, c_int, C.POINTER(c_double), c_void_p]),
 }
+
+
+class Xfer(C.Structure):
+    """chol_xfer_t (include/chol_b200.h)."""
+    _fields_ = [("dst", c_void_p), ("src", c_void_p), ("tile_bytes", c_ll), ("count", c_int), ("dst_stride", c_int),
+                ("src_stride", c_int), ("credit_value", C.c_uint32), ("credit", c_void_p), ("flag", c_void_p),
+                ("flag_value", C.c_uint32), ("reserved", C.c_uint32), ("stream", c_void_p)]
 
 
 class CholError(RuntimeError):

@@ -7,9 +7,11 @@ task lists of tile pointers) and then only enqueues kernels of ``libchol_b200.so
 ctypes; torch provides the buffers, streams, events and the NCCL broadcasts.
 
 Schedule (per rank; one rank per GPU, tiles 2D block-cyclic, see grid.py):
-  * panel stream (high priority): POTRF of the diagonal tile on its owner, broadcast of L_kk and
-    the inverted diagonal blocks down the owner's process column, TRSM of the panel tiles on
-    their owners (one grouped launch sequence), broadcast of the factored panel to all ranks;
+  * panel stream (high priority): POTRF of the diagonal tile on its owner, L_kk and the inverted
+    diagonal blocks pushed down the owner's process column, TRSM of the panel tiles on their
+    owners (one grouped launch sequence), the factored panel pushed to the ranks that read it
+    (transport.py: copy-engine peer copies + flag words, no kernel resident on a waiting GPU;
+    CHOL_PANEL_TRANSPORT=nccl keeps round 1's ncclBroadcast path for A/B runs);
   * update stream: the fused SYRK+GEMM trailing update of step k as grouped launches over every
     local tile (i,j), i>=j>k, in three stages: the diagonal tile (k+1,k+1) — POTRF(k+1) starts
     right after it —, the rest of column k+1 — then TRSM(k+1) —, and everything else, which
@@ -57,20 +59,22 @@ class TiledCholesky:
         # receive buffers (only with more than one rank): panel column k, two slots for lookahead
         self.panel = None
         self.diag = None
-        # How the factored panel reaches the other ranks: "nccl" = one ncclBroadcast per owner row
-        # (measured, default); "symm" = EXPERIMENTAL peer copies into symmetric receive buffers on
-        # the copy engines + stream-ordered flags, no kernel resident on the receivers (DESIGN.md
-        # section 8; written at the end of round 1 without GPU time left, not yet run on hardware).
-        self.transport = os.environ.get("CHOL_PANEL_TRANSPORT", "nccl") if (self.world > 1 and self.cuda) else "nccl"
-        if self.transport not in ("nccl", "symm"):
-            raise ValueError("CHOL_PANEL_TRANSPORT must be 'nccl' or 'symm'")
+        # How the factored panel reaches the other ranks: "peer" = pushes into IPC-mapped receive
+        # slots on the copy engines + flag words (transport.py, default on CUDA); "nccl" = one
+        # ncclBroadcast per owner row (round 1; also what the gloo CPU tests exercise).
+        default = "peer" if self.cuda else "nccl"
+        self.transport = os.environ.get("CHOL_PANEL_TRANSPORT", default) if self.world > 1 else "nccl"
+        if self.transport not in ("nccl", "peer"):
+            raise ValueError("CHOL_PANEL_TRANSPORT must be 'nccl' or 'peer'")
         self.nslots = 2
+        self.tr = None
         if self.world > 1:
-            if self.transport == "symm":
-                self._setup_symm_panel()
+            if self.transport == "peer":
+                self.tr = self._make_transport()
+                self.nslots = self.tr.nslots
             else:
                 self.panel = torch.empty((2, max(nt - 1, 1), b, b), **f64)
-            self.diag = torch.empty((b, b), **f64)
+                self.diag = torch.empty((b, b), **f64)
         self._col_groups = None
         if self.world > 1 and self.grid.P > 1:
             # dist.new_group is collective over ALL ranks: create every column group here, in the
@@ -81,8 +85,29 @@ class TiledCholesky:
         if self.cuda:
             self.s_update = torch.cuda.Stream(self.dev)
             self.s_panel = torch.cuda.Stream(self.dev, priority=-1)
+            if self.tr is not None:
+                # one send stream per peer (copies to different peers run on different copy engines)
+                # and one for the credit words, so neither ever sits in front of a kernel
+                self.s_sends = {r: torch.cuda.Stream(self.dev, priority=-1) for r in range(self.world) if r != self.rank}
+                self.s_credit = torch.cuda.Stream(self.dev, priority=-1)
         else:
             self.s_update = self.s_panel = None
+            self.s_sends, self.s_credit = {}, None
+
+    def _make_transport(self):
+        """The peer-push transport of this geometry (tests substitute a shared-memory double)."""
+        from .transport import PeerTransport
+        return PeerTransport(self.nt, self.b, self.grid, self.rank, self.work.numel(), self.group)
+
+    def _send_stream_of(self, r: int) -> int:
+        return self.s_sends[r].cuda_stream if self.s_sends else 0
+
+    def close(self) -> None:
+        """Release the transport's IPC mappings (collective over the ranks).  Optional: process exit
+        does the same."""
+        if self.tr is not None:
+            self.tr.close()
+            self.tr = None
 
     # ---- kernel entry points (the C ABI); tests override these on CPU tensors ----------------
     def _potrf_workspace(self, b: int) -> int:
@@ -91,8 +116,8 @@ class TiledCholesky:
     def _k_potrf(self, a_ptr: int, info_base: int, st: int) -> None:
         _lib.call("chol_potrf_tile", self.b, a_ptr, self.b, self.work.data_ptr(), self.d_info.data_ptr(), info_base, st)
 
-    def _k_trsm_panel(self, l_ptr: int, tiles_ptr: int, ntiles: int, st: int) -> None:
-        _lib.call("chol_trsm_tiles", self.b, l_ptr, self.b, self.work.data_ptr(), tiles_ptr, ntiles, self.b, None, st)
+    def _k_trsm_panel(self, l_ptr: int, work_ptr: int, tiles_ptr: int, ntiles: int, st: int) -> None:
+        _lib.call("chol_trsm_tiles", self.b, l_ptr, self.b, work_ptr, tiles_ptr, ntiles, self.b, None, st)
 
     def _k_update(self, tasks_ptr: int, ntasks: int, st: int) -> None:
         b = self.b
@@ -126,7 +151,10 @@ class TiledCholesky:
             ptr[rows] = base_local + (self.lay.col_start[k] + rows - k) * tb
             return ptr
         slot, _ = panel_slots(nt, self.grid.P, k)
-        pbase = self.panel.data_ptr() + (k % self.nslots) * self.panel.stride(0) * 8
+        if self.tr is not None:
+            pbase = self.tr.panel_slot_ptr(k)
+        else:
+            pbase = self.panel.data_ptr() + (k % self.nslots) * self.panel.stride(0) * 8
         mine_col = (k % self.grid.Q) == self.lay.q
         for i in range(k + 1, nt):
             if mine_col and i % self.grid.P == self.lay.p:
@@ -260,7 +288,15 @@ class TiledCholesky:
         if is_diag:
             self._k_potrf(self.A.tile_ptr(k, k), k * self.b, st)
         self._l_ptr = self.A.tile_ptr(k, k) if is_diag else 0
+        self._w_ptr = self.work.data_ptr()
         if g.P > 1 and in_col and k + 1 < nt:
+            if self.tr is not None:
+                if is_diag:
+                    self.tr.send_diag(k, self._l_ptr, self._w_ptr, st, self._send_stream_of)
+                elif self.rank in self.tr.diag_readers(k):
+                    self.tr.wait_diag(k, st)
+                    self._l_ptr, self._w_ptr = self.tr.diag_tile_ptr(k), self.tr.diag_work_ptr(k)
+                return
             cg = self._column_group(kq)
             ltile = self.A.tile(k, k) if is_diag else self.diag
             self._bcast(ltile, kp, cg)
@@ -277,12 +313,16 @@ class TiledCholesky:
         if factor:
             toff, cnt = self.step_trsm[k]
             if cnt:
-                self._k_trsm_panel(self._l_ptr, self.d_trsm_ptrs.data_ptr() + toff * 8, cnt, st)
+                self._k_trsm_panel(self._l_ptr, self._w_ptr, self.d_trsm_ptrs.data_ptr() + toff * 8, cnt, st)
         if self.world > 1 and k + 1 < nt:
-            _, groups = panel_slots(nt, g.P, k)
-            if self.transport == "symm":
-                self._send_panel_symm(k, groups)
+            if self.tr is not None:
+                if kq == lay.q:
+                    rows = lay.rows_in_col(k, k)
+                    if len(rows):
+                        self.tr.send_panel(k, self.A.tile_ptr(rows[0], k), st, self._send_stream_of)
+                self.tr.wait_panel(k, st)
                 return
+            _, groups = panel_slots(nt, g.P, k)
             for p, first, cnt in groups:
                 if cnt == 0:
                     continue
@@ -294,49 +334,12 @@ class TiledCholesky:
                     buf = self.panel[k % self.nslots, first:first + cnt]
                 self._bcast(buf, root, self.group)
 
-    # ---- experimental copy-engine transport (CHOL_PANEL_TRANSPORT=symm) --------------------------
-    def _setup_symm_panel(self) -> None:
-        """Symmetric receive buffers: every rank maps every peer's panel buffer.  Q+P+2 slots: a
-        rank owns a panel at least every Q steps and can only produce panel j after finishing its
-        update j-2, so nobody runs more than Q+1 (+P near the ragged end) steps ahead of a reader."""
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
-        nt, b = self.nt, self.b
-        self.nslots = max(2, min(max(nt - 1, 1), self.grid.Q + self.grid.P + 2))
-        self.panel = symm_mem.empty((self.nslots, max(nt - 1, 1), b, b), dtype=torch.float64, device=self.dev)
-        self._symm = symm_mem.rendezvous(self.panel, self.group if self.group is not None else dist.group.WORLD)
-        self._peer_panel = [self._symm.get_buffer(r, tuple(self.panel.shape), torch.float64) if r != self.rank else None
-                            for r in range(self.world)]
-        # one send stream per peer: the copies to different peers run on different copy engines / links
-        self.s_sends = [torch.cuda.Stream(self.dev) if r != self.rank else None for r in range(self.world)]
-
-    def _send_panel_symm(self, k: int, groups) -> None:
-        """Owner: after its TRSM, one peer copy per rank (copy engines over NVLink), each on that
-        peer's send stream and followed by that peer's flag.  Receiver: wait for the flag of each owner on the panel
-        stream.  Must be called with the panel stream current."""
-        g, lay = self.grid, self.lay
-        kq, slot = k % g.Q, k % self.nslots
-        for p, first, cnt in groups:
-            if cnt and g.rank_of(p, kq) == self.rank:
-                s0 = lay.index(lay.rows_in_col(k, k)[0], k)
-                src = self.A.buf[s0:s0 + cnt]
-                done = torch.cuda.Event()
-                done.record(self.s_panel)
-                for r in range(self.world):
-                    if r == self.rank:
-                        continue
-                    self.s_sends[r].wait_event(done)
-                    with torch.cuda.stream(self.s_sends[r]):
-                        self._peer_panel[r][slot, first:first + cnt].copy_(src, non_blocking=True)
-                        self._symm.put_signal(r, 0)
-        for p, first, cnt in groups:
-            root = g.rank_of(p, kq)
-            if cnt and root != self.rank:
-                self._symm.wait_signal(root, 0)
-
     def _run(self, update_tasks_ptr: int, factor: bool, pre_update=None, post_panel=None, step0_gates=None) -> None:
         nt = self.nt
         cuda = self.cuda
+        tr = self.tr
+        if tr is not None:
+            tr.begin_run()
         if cuda:
             cur = torch.cuda.current_stream(self.dev)
             self.s_update.wait_stream(cur)
@@ -362,11 +365,17 @@ class TiledCholesky:
                     ev_panel = torch.cuda.Event()
                     ev_panel.record(self.s_panel)
                 self.s_update.wait_event(ev_panel)
+                if tr is not None and (k % self.grid.Q) == self.lay.q:
+                    # this rank's TRSM k is enqueued: the L_kk slot it read may be overwritten
+                    self.s_credit.wait_event(ev_panel)
+                    tr.release_diag(k, self.s_credit.cuda_stream)
                 if post_panel is not None:
                     post_panel(k, ev_panel)
             else:
                 self._panel_potrf(k, factor)
                 self._panel_rest(k, factor)
+                if tr is not None and (k % self.grid.Q) == self.lay.q:
+                    tr.release_diag(k, 0)
             # ---- trailing update k
             st = self._stream_ptr(self.s_update)
             if pre_update is not None:
@@ -376,6 +385,8 @@ class TiledCholesky:
             if not cuda:
                 if ntot:
                     self._k_update(base, ntot, st)
+                if tr is not None:
+                    tr.release_panel(k, 0)
                 continue
             with torch.cuda.stream(self.s_update):
                 gated = k == 0 and bool(step0_gates)
@@ -386,6 +397,7 @@ class TiledCholesky:
                     if ntot:
                         self._k_update(base, ntot, st)
                     ev_diag = ev_col = ev_upd[k % ns] = self._record()
+                    self._release_panel(k, ev_upd[k % ns])
                     continue
                 # lookahead: (1) the diagonal tile of column k+1 so POTRF(k+1) can start, (2) the rest
                 # of column k+1 so TRSM(k+1) can start, (3) everything else, overlapped with panel k+1.
@@ -407,13 +419,23 @@ class TiledCholesky:
                 elif ntot > na:
                     self._k_update(base + na * 32, ntot - na, st)
                 ev_upd[k % ns] = self._record()
+                self._release_panel(k, ev_upd[k % ns])
         if cuda:
             cur.wait_stream(self.s_update)
             cur.wait_stream(self.s_panel)
-            if self.transport == "symm":
-                for s_ in self.s_sends:
-                    if s_ is not None:
-                        cur.wait_stream(s_)
+            if tr is not None:
+                for s_ in self.s_sends.values():
+                    cur.wait_stream(s_)
+                cur.wait_stream(self.s_credit)
+                tr.end_run(cur.cuda_stream)
+        elif tr is not None:
+            tr.end_run(0)
+
+    def _release_panel(self, k: int, ev) -> None:
+        """Update k is enqueued (event `ev`): tell the owners that panel slot k % nslots is free."""
+        if self.tr is not None:
+            self.s_credit.wait_event(ev)
+            self.tr.release_panel(k, self.s_credit.cuda_stream)
 
     def _record(self):
         ev = torch.cuda.Event()

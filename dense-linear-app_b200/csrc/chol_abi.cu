@@ -1,13 +1,12 @@
 // chol_abi.cu — the C ABI of libchol_b200.so (see include/chol_b200.h for the contract and
 // the reference interfaces each entry point replaces).  Host code here only validates
 // arguments and enqueues kernels; there is no CPU arithmetic and no CPU fallback.
-#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
-#include <string>
 
+#include "abi_common.cuh"
 #include "aux.cuh"
 #include "batched.cuh"
 #include "gemm_dmma.cuh"
@@ -15,29 +14,21 @@
 
 using namespace chol;
 
+namespace chol_abi {
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+}  // namespace chol_abi
+using namespace chol_abi;
+
 namespace {
 
-thread_local std::string g_err;
-std::atomic<unsigned long long> g_launches{0};  // kernels enqueued by this library (chol_launch_count)
 std::mutex g_mu;
 bool g_force_wide = false;  // CHOL_GEMM_WIDE=1: use the 128x128 shape everywhere (A/B experiments)
 bool g_inited[64] = {false};
 
-int fail_cuda(cudaError_t e, const char* where) {
-    g_err = std::string(where) + ": " + cudaGetErrorString(e);
-    return int(e) > 0 ? int(e) : 1;
-}
-int fail_arg(int idx, const char* fn, const char* what) {
-    g_err = std::string(fn) + ": bad argument " + std::to_string(idx) + " (" + what + ")";
-    return -idx;
-}
-#define CHECK_LAUNCH(where)                                      \
-    do {                                                         \
-        cudaError_t e__ = cudaGetLastError();                    \
-        if (e__ != cudaSuccess) return fail_cuda(e__, where);    \
-        g_launches.fetch_add(1, std::memory_order_relaxed);      \
-    } while (0)
+}  // namespace
 
+namespace chol_abi {
 int ensure_init() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -68,6 +59,9 @@ int ensure_init() {
     g_inited[dev] = true;
     return 0;
 }
+}  // namespace chol_abi
+
+namespace {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

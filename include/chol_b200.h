@@ -116,6 +116,55 @@ int chol_gemm_tile(int b, const double* Ai, int ldai, const double* Aj, int ldaj
 int chol_potrf_batched(int n, int batch, double* A, int lda, long long stride,
                        int* d_info, void* stream);
 
+/* ---- panel transport between the GPUs of one box ----------------------- */
+
+/* The reference leaves the movement of tiles between workers to StarPU/MPI (descriptor grid p,q:
+ * V6:44-45) or to the ArmoniK object store (W2:186,261).  Here the factored panel is PUSHED into
+ * receive slots of the ranks that read it, over NVLink with the copy engines, and announced by a
+ * flag word; no kernel is resident on a waiting GPU.  One process per GPU.
+ *
+ * chol_peer_alloc   cudaMalloc'ed, zero-filled buffer that can be exported to other processes.
+ * chol_peer_export  64-byte CUDA IPC handle of such a buffer (send it to the peers by any means).
+ * chol_peer_open    map a peer's buffer from its handle (enables P2P access); chol_peer_close unmaps.
+ */
+#define CHOL_IPC_HANDLE_BYTES 64
+int chol_peer_alloc(size_t bytes, void** out);
+int chol_peer_free(void* p);
+int chol_peer_export(void* p, void* handle64);
+int chol_peer_open(const void* handle64, void** out);
+int chol_peer_close(void* p);
+
+/* One push: `count` tiles of `tile_bytes` bytes from local `src` (tiles `src_stride` tiles apart) to
+ * the peer-mapped `dst` (`dst_stride` apart) on `stream`, after (optionally) waiting until the LOCAL
+ * word *credit has reached credit_value (the reader has released the slot), followed (optionally)
+ * by raising the PEER-mapped word *flag to flag_value.  Flag comparisons are cyclic:
+ * (int32)(*word - value) >= 0. */
+typedef struct chol_xfer {
+    void*           dst;
+    const void*     src;
+    long long       tile_bytes;
+    int             count;
+    int             dst_stride;
+    int             src_stride;
+    uint32_t        credit_value;
+    const uint32_t* credit;
+    uint32_t*       flag;
+    uint32_t        flag_value;
+    uint32_t        reserved;
+    void*           stream;
+} chol_xfer_t;
+
+/* Enqueue `n` pushes; each first waits for everything enqueued so far on `ready_stream` (the
+ * stream that produced the data).  Copies use the copy engines (no SM work besides the one-warp
+ * flag store). */
+int chol_peer_send(const chol_xfer_t* xf, int n, void* ready_stream);
+/* Make `stream` wait until (int32)(*flag - value) >= 0.  `flag` is LOCAL device memory written by a
+ * peer.  A stream memory operation (cuStreamWaitValue32): nothing runs on the SMs while waiting. */
+int chol_flag_wait(const uint32_t* flag, uint32_t value, void* stream);
+/* Raise up to 16 (peer-mapped or local) flag words to `value`, ordered after the work already
+ * enqueued on `stream`.  `flags` is a HOST array of device pointers. */
+int chol_flag_post(uint32_t* const* flags, int n, uint32_t value, void* stream);
+
 /* ---- generators and checks (V6:46, V6:51, V6:72-86; off the timed path) ----------- */
 
 /* dplgsy-like tile generator (V6:46 CHAMELEON_dplgsy_Tile(bump, ChamLower, desc, seed)):

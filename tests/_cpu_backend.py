@@ -19,7 +19,11 @@ class OracleBackedCholesky(TiledCholesky):
         if info and int(self.d_info[0]) == 0:
             self.d_info[0] = info_base + info
 
-    def _k_trsm_panel(self, l_ptr, tiles_ptr, ntiles, st):
+    def _make_transport(self):
+        from _shm_transport import ShmTransport
+        return ShmTransport(self.nt, self.b, self.grid, self.rank, self.work.numel(), self.group)
+
+    def _k_trsm_panel(self, l_ptr, work_ptr, tiles_ptr, ntiles, st):
         ptrs = (C.c_int64 * ntiles).from_address(tiles_ptr)
         for t in range(ntiles):
             O.lib().oracle_trsm_tile(self.b, self.b, l_ptr, self.b, ptrs[t], self.b)

@@ -7,8 +7,9 @@ collectives, peer copies and flags become nodes of ONE dependency graph over all
   * an NCCL-style broadcast: every participant posts (node) and completes (node); a completion
     depends on every participant's post.  Collectives are matched per communicator by call order,
     a missing or mis-ordered participant is reported as a hang;
-  * symmetric-memory flags: the k-th ``put_signal(src -> dst)`` releases the k-th
-    ``wait_signal(dst <- src)``; a put waits for the previous flag of the same pair to be consumed.
+  * the peer-push transport (transport.py) with its primitives recorded: a push is a node on the send
+    stream that reads the owner's tiles and WRITES the reader's slot; a flag wait depends on the post
+    of the same (rank, word, value) — a wait whose post never happens is reported as a hang.
 
 Checks: the graph is acyclic (no deadlock), and any two accesses to the same tile/buffer of the same
 rank with at least one write are ordered by reachability (no race) — including a peer's remote write
@@ -21,6 +22,7 @@ import numpy as np
 import torch
 
 from dense_linear_app_b200.cholesky import TiledCholesky
+from dense_linear_app_b200.transport import PeerTransport
 
 
 class Graph:
@@ -28,7 +30,7 @@ class Graph:
         self.kind, self.rank, self.preds, self.acc = [], [], [], []   # acc[n] = [(region, is_write)]
         self.coll = {}      # (comm key, seq) -> [(rank, post, done)]
         self.comm_size = {}
-        self.puts, self.waits = {}, {}   # (src, dst, ch) -> [node]
+        self.posts, self.waits = {}, {}   # (rank, word, value) -> node / [nodes]
 
     def node(self, kind, rank, reads=(), writes=()):
         self.kind.append(kind)
@@ -50,14 +52,13 @@ class Graph:
             for _, post, _ in parts:
                 for _, _, done in parts:
                     self.edge(post, done)
-        for key in set(self.puts) | set(self.waits):
-            p, w = self.puts.get(key, []), self.waits.get(key, [])
-            if len(p) != len(w):
-                problems.append(f"flags {key}: {len(p)} puts but {len(w)} waits")
-            for k in range(min(len(p), len(w))):
-                self.edge(p[k], w[k])
-                if k + 1 < len(p):
-                    self.edge(w[k], p[k + 1])
+        for key, ws in self.waits.items():
+            if key not in self.posts:
+                if key[2] != 0:                 # value 0 = the zero-filled initial state
+                    problems.append(f"flag wait {key} (rank, word, value) is never posted (hang)")
+                continue
+            for w in ws:
+                self.edge(self.posts[key], w)
         return problems
 
     def ancestors(self):
@@ -99,10 +100,14 @@ class Graph:
         return bad
 
 
+STREAMS = {}
+
+
 class SimStream:
     def __init__(self, g, rank):
         self.g, self.rank, self.last = g, rank, None
         self.cuda_stream = id(self)
+        STREAMS[self.cuda_stream] = self
 
     def chain(self, n):
         self.g.edge(self.last, n)
@@ -139,26 +144,54 @@ def stream_ctx(s):
         CUR.pop()
 
 
-class SymmHandle:
-    """Fake of the _SymmetricMemory handle: flags only."""
+class SimTransport(PeerTransport):
+    """transport.py with its primitives turned into graph nodes.  All ranks live in one process, so
+    the "peer-mapped" addresses are simply the addresses of the other ranks' buffers."""
 
-    def __init__(self, g, rank):
-        self.g, self.rank = g, rank
+    def __init__(self, sim, *a, nslots=None, credits=True, **k):
+        self.sim, self.credits = sim, credits
+        if nslots:
+            self.NSLOTS = nslots
+        super().__init__(*a, **k)
 
-    def put_signal(self, dst, ch=0, timeout_ms=0):
-        s = CUR[-1]
-        self.g.puts.setdefault((self.rank, dst, ch), []).append(s.chain(self.g.node("put", self.rank)))
+    def _open(self):
+        self.buf = torch.zeros(self.nbytes // 8 + 1, dtype=torch.float64)
+        self.local = self.buf.data_ptr()
 
-    def wait_signal(self, src, ch=0, timeout_ms=0):
-        s = CUR[-1]
-        self.g.waits.setdefault((src, self.rank, ch), []).append(s.chain(self.g.node("flagwait", self.rank)))
+    def connect(self, sims):
+        self.peer_base = {s.rank: s.tr.local for s in sims if s.rank != self.rank}
+
+    def _send(self, pushes, ready_stream, send_stream_of):
+        g, sim = self.sim.g, self.sim
+        ready = STREAMS[ready_stream].last
+        for p in pushes:
+            st = STREAMS[send_stream_of(p.peer)]
+            rd = {sim.region(p.src + t * p.src_stride * p.tile_bytes) for t in range(p.count)}
+            wr = {sim.region(self.peer_base[p.peer] + p.dst_off + t * p.dst_stride * p.tile_bytes)
+                  for t in range(p.count)}
+            n = st.chain(g.node("peer-copy", self.rank, rd, wr))
+            g.edge(ready, n)
+            if p.credit is not None and self.credits:
+                g.waits.setdefault((self.rank, p.credit, p.credit_value), []).append(n)
+            if p.flag is not None:
+                g.posts[(p.peer, p.flag, p.flag_value)] = st.chain(g.node("post", self.rank))
+
+    def _wait(self, flag, value, stream):
+        st = STREAMS[stream]
+        self.sim.g.waits.setdefault((self.rank, flag, value), []).append(st.chain(self.sim.g.node("flagwait", self.rank)))
+
+    def _post(self, targets, value, stream):
+        st = STREAMS[stream]
+        n = st.chain(self.sim.g.node("post", self.rank))
+        for r, f in targets:
+            self.sim.g.posts[(r, f, value)] = n
 
 
 class RankSim(TiledCholesky):
     """One rank of the simulated job.  `world_sims` (filled by simulate()) gives access to the peers'
     receive buffers for the symmetric transport."""
 
-    def __init__(self, g, A, lookahead=True, transport="nccl", nslots=None):
+    def __init__(self, g, A, lookahead=True, transport="nccl", nslots=None, credits=True):
         self.g = g
         self.A, self.nt, self.b = A, A.nt, A.b
         self.grid, self.rank, self.lay = A.grid, A.rank, A.layout
@@ -166,27 +199,25 @@ class RankSim(TiledCholesky):
         self.group, self.lookahead, self.transport = None, lookahead, transport
         self.update_events = None
         self.tile_bytes = self.b * self.b * 8
-        self.nslots = 2 if transport == "nccl" else (nslots or max(2, min(max(self.nt - 1, 1),
-                                                                          self.grid.Q + self.grid.P + 2)))
         self.work = torch.zeros(16, dtype=torch.float64)
         self.d_info = torch.zeros(1, dtype=torch.int32)
-        self.panel = torch.zeros((self.nslots, max(self.nt - 1, 1), self.b, self.b), dtype=torch.float64)
+        self.nslots, self.tr = 2, None
+        if transport == "peer":
+            self.tr = SimTransport(self, self.nt, self.b, self.grid, self.rank, self.work.numel(), nslots=nslots,
+                                   credits=credits)
+            self.nslots = self.tr.nslots
+        self.panel = torch.zeros((2, max(self.nt - 1, 1), self.b, self.b), dtype=torch.float64)
         self.diag = torch.zeros((self.b, self.b), dtype=torch.float64)
         self._col_groups = [("col", q) for q in range(self.grid.Q)]
         g.comm_size["world"] = self.world
         for q in range(self.grid.Q):
             g.comm_size[("col", q)] = self.grid.P
-        self._build_plan()
         self.s_update, self.s_panel = SimStream(g, self.rank), SimStream(g, self.rank)
-        self.s_sends = [SimStream(g, self.rank) if r != self.rank else None for r in range(self.world)]
+        self.s_sends = {r: SimStream(g, self.rank) for r in range(self.world) if r != self.rank}
+        self.s_credit = SimStream(g, self.rank)
         self.cur = SimStream(g, self.rank)
-        self._symm = SymmHandle(g, self.rank)
         self._seq = {}
         self.world_sims = None
-
-    @property
-    def _peer_panel(self):
-        return [s.panel if s.rank != self.rank else None for s in self.world_sims]
 
     # ---- addresses -> (rank, buffer, tile) regions
     def region(self, ptr):
@@ -195,6 +226,13 @@ class RankSim(TiledCholesky):
             for name, t in (("A", sim.A.buf), ("P", sim.panel), ("D", sim.diag), ("W", sim.work)):
                 if t.data_ptr() <= ptr < t.data_ptr() + t.numel() * 8:
                     return (sim.rank, name, (ptr - t.data_ptr()) // tb if name in ("A", "P") else 0)
+            tr = sim.tr
+            if tr is not None and tr.local <= ptr < tr.local + tr.nbytes:
+                off = ptr - tr.local
+                if off >= tr.off_panel:
+                    return (sim.rank, "P", (off - tr.off_panel) // tb)
+                assert off >= tr.off_diag, "pointer into the flag words"
+                return (sim.rank, "D", (off - tr.off_diag) // tr.diag_stride)
         raise AssertionError("pointer outside every known buffer")
 
     def regions_of(self, t):
@@ -216,9 +254,9 @@ class RankSim(TiledCholesky):
         t = self.region(a_ptr)
         self.op("potrf", {t}, {t, (self.rank, "W", 0)})
 
-    def _k_trsm_panel(self, l_ptr, tiles_ptr, ntiles, st):
+    def _k_trsm_panel(self, l_ptr, work_ptr, tiles_ptr, ntiles, st):
         tl = {self.region(p) for p in (C.c_int64 * ntiles).from_address(tiles_ptr)}
-        self.op("trsm", tl | {self.region(l_ptr), (self.rank, "W", 0)}, tl)
+        self.op("trsm", tl | {self.region(l_ptr), self.region(work_ptr)}, tl)
 
     def _k_update(self, tasks_ptr, ntasks, st):
         rec = np.ctypeslib.as_array((C.c_int64 * (4 * ntasks)).from_address(tasks_ptr)).reshape(ntasks, 4)
@@ -238,34 +276,29 @@ class RankSim(TiledCholesky):
         self.g.coll.setdefault((key, seq), []).append((self.rank, post, done))
 
 
-def simulate(make_matrix, world, **kw):
-    """Run every rank's factor() schedule into one graph.  Returns (graph, problems, races)."""
+def simulate(make_matrix, world, runs=1, **kw):
+    """Run every rank's factor() schedule (`runs` times back to back) into one graph.  Returns
+    (graph, problems, races)."""
     g = Graph()
     sims = [RankSim(g, make_matrix(r), **kw) for r in range(world)]
-    real_copy = torch.Tensor.copy_
-    bufs = [(s.rank, s.panel.data_ptr(), s.panel.data_ptr() + s.panel.numel() * 8) for s in sims]
     for s in sims:
         s.world_sims = sims
+    for s in sims:
+        if s.tr is not None:
+            s.tr.connect(sims)
+        s._build_plan()            # needs every rank's buffers for the region lookup
 
-    def recording_copy(dst, src, non_blocking=False):
-        for r, lo, hi in bufs:
-            if lo <= dst.data_ptr() < hi:                      # a peer copy into rank r's receive buffer
-                sim = sims[CUR[-1].rank]
-                sim.op("peer-copy", sim.regions_of(src), sim.regions_of(dst))
-                return dst
-        return real_copy(dst, src, non_blocking)
-
-    saved = (torch.cuda.Event, torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream, torch.Tensor.copy_)
+    saved = (torch.cuda.Event, torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream)
     torch.cuda.Event, torch.cuda.stream = SimEvent, stream_ctx
     torch.cuda.current_stream = lambda *a, **k: CUR[-1]
-    torch.Tensor.copy_ = recording_copy
     try:
         for s in sims:
             CUR.clear()
             CUR.append(s.cur)
-            s._run(s.d_tasks.data_ptr(), factor=True)
+            for _ in range(runs):
+                s._run(s.d_tasks.data_ptr(), factor=True)
     finally:
-        torch.cuda.Event, torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream, torch.Tensor.copy_ = saved
+        torch.cuda.Event, torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream = saved
         CUR.clear()
     problems = g.link()
     anc, cyc = g.ancestors()

@@ -22,10 +22,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, P, Q, N, b, lookahead, bad):
+def _worker(rank, world, port, P, Q, N, b, lookahead, bad, transport="nccl"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CHOL_PANEL_TRANSPORT=transport)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from _cpu_backend import OracleBackedCholesky
@@ -38,6 +38,7 @@ def _worker(rank, world, port, P, Q, N, b, lookahead, bad):
         M = TileMatrix(desc, rank, "cpu").from_numpy(A)
         M0 = M.clone()
         ch = OracleBackedCholesky(M, lookahead=lookahead)
+        assert ch.transport == transport and (ch.tr is not None) == (transport == "peer")
         ch.factor()
         info = ch.info()
         if bad is not None:
@@ -59,6 +60,25 @@ def _worker(rank, world, port, P, Q, N, b, lookahead, bad):
             assert np.abs(blk - ref).max() <= 1e-13 * np.abs(Lref).max(), (rank, i, j)
         res = ch.residual(M0)
         assert res["fro"] < 1e-15 * 10 and res["inf"] < 1e-14, res
+        if transport == "peer":
+            # a second factorization through the same slots (next epoch of the flag counters), and
+            # the volume: every tile reaches P+Q-2 readers, not all P*Q-1
+            M.buf.copy_(TileMatrix(desc, rank, "cpu").from_numpy(A).buf)
+            ch.tr.pushed_bytes = 0
+            ch.factor()
+            assert ch.info() == 0
+            got2 = M.to_numpy()
+            assert np.array_equal(got2, got)
+            sent = torch.tensor([ch.tr.pushed_bytes], dtype=torch.int64)
+            recv = torch.tensor([ch.tr.bytes_received_per_run()], dtype=torch.int64)
+            dist.all_reduce(sent)
+            dist.all_reduce(recv)
+            assert int(sent) == int(recv)
+            tb = b * b * 8
+            ntl = nt * (nt - 1) // 2
+            diag_msgs = sum(len(ch.tr.diag_readers(k)) for k in range(nt - 1)) if P > 1 else 0
+            assert int(sent) <= ntl * (P + Q - 2) * tb + diag_msgs * (tb + ch.tr.work_bytes)
+            ch.close()
     finally:
         dist.destroy_process_group()
 
@@ -73,6 +93,20 @@ def _worker(rank, world, port, P, Q, N, b, lookahead, bad):
 def test_block_cyclic_schedule_gloo(P, Q, N, b, lookahead):
     world = P * Q
     mp.spawn(_worker, args=(world, _free_port(), P, Q, N, b, lookahead, None), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("P,Q,N,b,lookahead", [
+    (1, 2, 96, 16, True),
+    (2, 2, 116, 16, True),      # ragged edge
+    (2, 1, 80, 16, False),
+    (2, 4, 208, 16, True),      # the 8-GPU grid shape
+    (3, 2, 112, 16, True),      # P does not divide Q: the strided subsets are not "every other tile"
+])
+def test_peer_push_transport_shared_memory(P, Q, N, b, lookahead):
+    """The copy-engine transport's host logic (slots, reader subsets, credits, flag epochs) with
+    shared memory standing in for the IPC-mapped peer buffers."""
+    world = P * Q
+    mp.spawn(_worker, args=(world, _free_port(), P, Q, N, b, lookahead, None, "peer"), nprocs=world, join=True)
 
 
 def test_info_reduced_over_ranks_gloo():

@@ -17,7 +17,7 @@ class PlanOnly(TiledCholesky):
         self.A, self.nt, self.b = A, A.nt, A.b
         self.grid, self.rank, self.lay = A.grid, A.rank, A.layout
         self.dev, self.cuda, self.world = A.device, False, A.grid.size
-        self.group, self.lookahead, self.nslots, self.transport = None, True, 2, "nccl"
+        self.group, self.lookahead, self.nslots, self.transport, self.tr = None, True, 2, "nccl", None
         self.tile_bytes = self.b * self.b * 8
         self.panel = torch.empty((2, max(self.nt - 1, 1), self.b, self.b), dtype=torch.float64) if self.world > 1 else None
         self._build_plan()

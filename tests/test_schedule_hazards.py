@@ -78,7 +78,7 @@ class Probe(TiledCholesky):
         self.grid, self.rank, self.lay = A.grid, A.rank, A.layout
         self.dev, self.world = A.device, A.grid.size
         self.cuda = True                      # take the CUDA branches of _run, with the fakes below
-        self.group, self.lookahead, self.nslots, self.transport = None, lookahead, 2, "nccl"
+        self.group, self.lookahead, self.nslots, self.transport, self.tr = None, lookahead, 2, "nccl", None
         self.update_events = None
         self.tile_bytes = self.b * self.b * 8
         f64 = dict(dtype=torch.float64)
@@ -123,7 +123,7 @@ class Probe(TiledCholesky):
     def _k_potrf(self, a_ptr, info_base, st):
         self.op("potrf", st, {self.region(a_ptr)}, {self.region(a_ptr), ("W",), ("info",)})
 
-    def _k_trsm_panel(self, l_ptr, tiles_ptr, ntiles, st):
+    def _k_trsm_panel(self, l_ptr, work_ptr, tiles_ptr, ntiles, st):
         ptrs = (C.c_int64 * ntiles).from_address(tiles_ptr)
         tl = {self.region(p) for p in ptrs}
         self.op("trsm", st, tl | {self.region(l_ptr), ("W",)}, tl)

@@ -1,6 +1,7 @@
 """Whole-job checks of the multi-rank schedule on the CPU (tests/_schedule_sim.py): no deadlock, every
-collective matched on every participant, and no race anywhere — for the measured NCCL transport and for
-the experimental symmetric-memory transport, whose receive-slot count is exactly what this verifies."""
+collective matched on every participant, and no race anywhere — for the NCCL transport and for the
+peer-push transport (copy-engine pushes, flag words, credits), including back-to-back factorizations
+through the same receive slots."""
 import os
 import sys
 
@@ -25,19 +26,21 @@ def test_nccl_schedule_whole_job(P, Q, nt, lookahead):
     assert sum(k == "bcast-done" for k in g.kind) > 0
 
 
-@pytest.mark.parametrize("P,Q,nt", [(1, 2, 9), (2, 2, 11), (2, 4, 17), (2, 4, 5)])
-def test_symm_transport_whole_job(P, Q, nt):
-    """Peer copies + flags with Q+P+2 receive slots: matched flags, no deadlock, and in particular no
-    remote write into a slot that a slower rank is still reading."""
-    g, problems, races = simulate(maker(P, Q, nt), P * Q, lookahead=True, transport="symm")
+@pytest.mark.parametrize("P,Q,nt", [(1, 2, 9), (2, 2, 11), (2, 4, 17), (2, 4, 5), (3, 2, 10), (2, 1, 6)])
+@pytest.mark.parametrize("runs", [1, 2])
+def test_peer_transport_whole_job(P, Q, nt, runs):
+    """Pushes + flags + credits: every wait has its post, no deadlock, and no remote write into a
+    slot (panel or L_kk) that a slower rank is still reading — also across two factorizations."""
+    g, problems, races = simulate(maker(P, Q, nt), P * Q, runs=runs, lookahead=True, transport="peer")
     assert problems == []
     assert races == []
-    assert sum(k == "peer-copy" for k in g.kind) > 0 and sum(k == "put" for k in g.kind) > 0
+    assert sum(k == "peer-copy" for k in g.kind) > 0 and sum(k == "flagwait" for k in g.kind) > 0
 
 
-def test_symm_transport_needs_more_than_two_slots():
-    """With only the two slots the NCCL path uses, one-sided writes DO race with a lagging reader —
-    the reason the symmetric transport allocates Q+P+2 (and the proof that the checker sees it)."""
-    g, problems, races = simulate(maker(2, 4, 17), 8, lookahead=True, transport="symm", nslots=2)
-    assert problems == []
-    assert any(reg[1] == "P" for reg, _, _ in races)
+def test_peer_transport_two_slots_are_safe_with_credits_only():
+    """Two receive slots are race-free because the sender waits for the reader's credit; without
+    the credits the one-sided writes DO race with a lagging reader (proof that the checker sees it)."""
+    g, problems, races = simulate(maker(2, 4, 17), 8, lookahead=True, transport="peer", nslots=2)
+    assert problems == [] and races == []
+    g, problems, races = simulate(maker(2, 4, 17), 8, lookahead=True, transport="peer", nslots=2, credits=False)
+    assert any(reg[1] in ("P", "D") for reg, _, _ in races)

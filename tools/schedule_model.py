@@ -44,7 +44,7 @@ def model(P, Q, nt, a, transport="nccl"):
         elif kind == "peer-copy":
             ntiles = sum(1 for (reg, w) in acc if w)
             dur[n] = 5e-6 + ntiles * tile_bytes / (a.p2p_gbs * 1e9)
-        elif kind in ("put", "flagwait"):
+        elif kind in ("post", "flagwait"):
             dur[n] = 3e-6
     # longest path (nodes are created in a topological-compatible order per rank, but cross-rank edges
     # need a real topological pass)
@@ -87,7 +87,7 @@ def main():
     print(f"N={a.nt * a.tile} tile={a.tile}: critical-path model (update {a.update_tflops} TFLOP/s per GPU)")
     t1 = None
     for (P, Q) in ((1, 1), (1, 2), (2, 2), (2, 4)):
-        for tr in (("nccl",) if P * Q == 1 else ("nccl", "symm")):
+        for tr in (("nccl",) if P * Q == 1 else ("nccl", "peer")):
             t, busy_max, busy_avg = model(P, Q, a.nt, a, tr)
             t1 = t1 or t
             print(f"  {P}x{Q} {tr:5s}: {t * 1e3:8.1f} ms  {flops / t / 1e12:7.1f} TFLOP/s  efficiency {t1 / (P * Q) / t * 100:5.1f} %"
