@@ -2,6 +2,7 @@
 // workload: one POTRF task per small tile, C1:139-141 / W2:179-268, here one CTA per matrix).
 #pragma once
 #include <cuda_runtime.h>
+#include "gemm_dmma.cuh"
 #include "panel.cuh"
 
 namespace chol {
@@ -88,6 +89,247 @@ potrf_batched_global_kernel(int n, double* __restrict__ Abase, int lda, long lon
                 A[size_t(o + w + jj) * lda + (o + w + ii)] -= s;
             }
         }
+        __syncthreads();
+    }
+    if (tid == 0) d_info[blockIdx.x] = s_info;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// n % 32 == 0, 32 <= n <= 256: LEFT-LOOKING blocked kernel on the DMMA pipe, several matrices in
+// flight per SM (configs[4]: 10 000 x 256).  One CTA (4 consumer warps + 1 producer warp) per
+// matrix; for every 32-wide block column j:
+//   1. update   C(R x 32) = A(r0:, j) - L(r0:, 0:K) L(r0:r0+32, 0:K)^T,  K = 32 j, on m8n8k4 DMMAs:
+//      the K dimension streams through a ring of shared-memory slabs (8 columns of L each) filled by
+//      the producer warp with TMA bulk copies out of this matrix's own, L2-hot, earlier columns; a
+//      consumer warp owns one 32 x 32 block of C in registers.  Two passes of at most 128 rows keep
+//      the accumulators at 32 doubles per thread (-> 4 CTAs per SM); the B operand (rows r0..r0+31)
+//      is part of the first pass' slab and is re-staged for the second;
+//   2. potrf32  the diagonal block, one warp, a row per lane in registers, warp shuffles;
+//   3. trsm     the rows below it, one thread per row by forward substitution in axpy form against
+//      the shared-memory copy of L_jj (more accurate than multiplying by an inverse, and it needs
+//      none), written straight back to global memory.
+// The matrix never has to fit in shared memory; HBM sees each lower-triangle element once in and
+// once out (8 n (n+1) bytes per matrix = the algorithmic minimum), the re-reads of L hit L2.
+constexpr int BLW = 32;                 // block-column width
+constexpr int BLK = 8;                  // slab depth
+constexpr int BL_ROWS = 128;            // rows per pass
+constexpr int BL_PITCH = BL_ROWS + 4;   // doubles; same conflict-free LDS.128 pattern as gemm_dmma.cuh
+constexpr int BL_CONSUMERS = 4;
+constexpr int BL_THREADS = (BL_CONSUMERS + 1) * 32;
+constexpr int BL_LP = 34;               // pitch of the column-major shared copy of L_jj (even: double2 loads)
+constexpr int BATCHED_LL_MAX_N = 256;
+
+template <int STAGES>
+struct BatchedLL {
+    static constexpr int SLAB = BLK * BL_PITCH;
+    static constexpr size_t SMEM = size_t(STAGES * SLAB + BLW * BL_LP + BLW) * 8 + 2 * STAGES * 8 + 16;
+};
+
+// In-register Cholesky of a 32x32 block, lane = row (a[j] = element (lane, j), upper part ignored).
+// Pivot through rsqrt: piv = d * rsqrt(d), 1/piv = rsqrt(d) — one special-function sequence instead of
+// a square root and a division on the dependent chain.  Returns the 1-based index of the first
+// non-positive (or NaN) pivot, 0 if none; inv_out = 1 / l_cc of this lane's own diagonal element.
+__device__ __forceinline__ int potrf32_regs(double (&a)[SB], double& inv_out) {
+    const int lane = threadIdx.x & 31;
+    int info = 0;
+    inv_out = 0.0;
+#pragma unroll
+    for (int c = 0; c < SB; ++c) {
+        const double d = __shfl_sync(0xffffffffu, a[c], c);
+        if (!(d > 0.0) && info == 0) info = c + 1;
+        const double inv = rsqrt(d);
+        const double piv = d * inv;
+        const double l = (lane == c) ? piv : a[c] * inv;
+        a[c] = l;
+        if (lane == c) inv_out = inv;
+#pragma unroll
+        for (int j = c + 1; j < SB; ++j) {
+            const double ljc = __shfl_sync(0xffffffffu, l, j);
+            a[j] = fma(-l, ljc, a[j]);
+        }
+    }
+    return info;
+}
+
+template <int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(BL_THREADS, MIN_CTAS)
+potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long stride, int* __restrict__ d_info) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    constexpr int SLAB = BatchedLL<STAGES>::SLAB;
+    double* slabs = reinterpret_cast<double*>(smem_dyn);
+    double* Lcm = slabs + STAGES * SLAB;           // L_jj, column-major, pitch BL_LP
+    double* invd = Lcm + BLW * BL_LP;              // 1 / l_cc
+    uint64_t* bars = reinterpret_cast<uint64_t*>(invd + BLW);   // [0,STAGES) full, [STAGES,2*STAGES) empty
+    __shared__ int s_info;
+
+    double* A = Abase + size_t(blockIdx.x) * size_t(stride);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
+    const int g = lane >> 2, t = lane & 3;
+
+    if (tid == 0) {
+        s_info = 0;
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[STAGES + s]), BL_CONSUMERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int it = 0;                                     // slabs streamed so far (same count in every warp)
+    const int nb = n / BLW;
+    for (int j = 0; j < nb; ++j) {
+        const int r0 = j * BLW;
+        const int R = n - r0;
+        const int nslab = r0 / BLK;                 // K = 32 j columns of L to the left
+        if (nslab > 0) {
+            for (int pass = 0; pass < 2; ++pass) {
+                const int prow = pass == 0 ? min(R, BL_ROWS) : R - BL_ROWS;   // rows of C in this pass
+                if (prow <= 0) break;
+                const int row_first = pass == 0 ? r0 : r0 + BL_ROWS;
+                if (warp == BL_CONSUMERS) {
+                    // ---------------- producer: slab = [32 B-rows | the pass' own rows] x 8 columns
+                    const int col = lane & 7;
+                    const int part = lane >> 3;     // 0: B rows (pass 1) / all rows (pass 0); 1: own rows of pass 1
+                    const uint32_t tx = uint32_t(BLK) * uint32_t(pass == 0 ? prow : BLW + prow) * 8u;
+                    for (int s = 0; s < nslab; ++s, ++it) {
+                        const int st = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(smem_u32(&bars[STAGES + st]), ph ^ 1);
+                        const uint32_t full = smem_u32(&bars[st]);
+                        if (lane == 0) mbar_expect_tx(full, tx);
+                        __syncwarp();
+                        double* dst = slabs + st * SLAB + col * BL_PITCH;
+                        const double* src = A + size_t(s * BLK + col) * lda;
+                        if (pass == 0) {
+                            if (part == 0) bulk_g2s(smem_u32(dst), src + r0, uint32_t(prow) * 8u, full);
+                        } else if (part == 0) {
+                            bulk_g2s(smem_u32(dst), src + r0, uint32_t(BLW) * 8u, full);
+                        } else if (part == 1) {
+                            bulk_g2s(smem_u32(dst + BLW), src + row_first, uint32_t(prow) * 8u, full);
+                        }
+                    }
+                } else {
+                    // ---------------- consumers: one 32 x 32 block of C per warp
+                    // pass 0: warp w -> rows [32 w, 32 w + 32) of the slab; pass 1: warps 1..3 -> own rows
+                    const int blk = pass == 0 ? warp : warp - 1;
+                    const bool has = blk >= 0 && blk * BLW < prow;
+                    const int slab_row = pass == 0 ? blk * BLW : BLW + blk * BLW;
+                    double acc[2][2][2][2][2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int mp = 0; mp < 2; ++mp)
+#pragma unroll
+                                for (int np = 0; np < 2; ++np) acc[q][r][mp][np][0] = acc[q][r][mp][np][1] = 0.0;
+                    for (int s = 0; s < nslab; ++s, ++it) {
+                        const int st = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(smem_u32(&bars[st]), ph);
+                        if (has) {
+                            const double* sl = slabs + st * SLAB + t * BL_PITCH + 2 * g;
+#pragma unroll
+                            for (int kk = 0; kk < BLK; kk += 4) {
+                                double2 a[2], b[2];
+#pragma unroll
+                                for (int q = 0; q < 2; ++q)
+                                    a[q] = *reinterpret_cast<const double2*>(sl + kk * BL_PITCH + slab_row + q * 16);
+#pragma unroll
+                                for (int r = 0; r < 2; ++r)
+                                    b[r] = *reinterpret_cast<const double2*>(sl + kk * BL_PITCH + r * 16);
+#pragma unroll
+                                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                                    for (int r = 0; r < 2; ++r) {
+                                        dmma884(acc[q][r][0][0][0], acc[q][r][0][0][1], a[q].x, b[r].x);
+                                        dmma884(acc[q][r][0][1][0], acc[q][r][0][1][1], a[q].x, b[r].y);
+                                        dmma884(acc[q][r][1][0][0], acc[q][r][1][0][1], a[q].y, b[r].x);
+                                        dmma884(acc[q][r][1][1][0], acc[q][r][1][1][1], a[q].y, b[r].y);
+                                    }
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + st]));
+                    }
+                    if (has) {
+                        // C = A - acc, 2 consecutive rows per access; the diagonal block keeps its
+                        // strict upper triangle untouched
+                        const bool diag = pass == 0 && blk == 0;
+                        double* gC = A + size_t(r0) * lda + row_first + blk * BLW;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+#pragma unroll
+                            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                                    for (int np = 0; np < 2; ++np) {
+                                        const int rl = q * 16 + 2 * g;
+                                        const int cl = r * 16 + 4 * t + 2 * e + np;
+                                        double* ptr = gC + size_t(cl) * lda + rl;
+                                        if (diag && rl < cl) {
+                                            if (rl + 1 == cl) ptr[1] -= acc[q][r][1][np][e];
+                                            continue;
+                                        }
+                                        double2 v = *reinterpret_cast<const double2*>(ptr);
+                                        v.x -= acc[q][r][0][np][e];
+                                        v.y -= acc[q][r][1][np][e];
+                                        *reinterpret_cast<double2*>(ptr) = v;
+                                    }
+                    }
+                }
+            }
+            __syncthreads();    // the updated block column is visible to the whole CTA
+        }
+        // ---- diagonal block: one warp, registers + shuffles
+        if (warp == 0) {
+            double a[SB];
+            const double* gD = A + size_t(r0) * lda + r0 + lane;
+#pragma unroll
+            for (int c = 0; c < SB; ++c) a[c] = (lane >= c) ? gD[size_t(c) * lda] : 0.0;
+            double inv;
+            const int info = potrf32_regs(a, inv);
+            if (info != 0 && lane == 0 && s_info == 0) s_info = r0 + info;
+            double* gDw = A + size_t(r0) * lda + r0 + lane;
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                if (lane >= c) gDw[size_t(c) * lda] = a[c];
+                Lcm[c * BL_LP + lane] = a[c];
+            }
+            invd[lane] = inv;
+        }
+        __syncthreads();
+        // ---- rows below: X L_jj^T = C by forward substitution, one thread per row
+        for (int row = r0 + BLW + tid; row < n; row += BL_THREADS) {
+            // compiler barrier: without it the (loop-invariant) shared-memory loads of L_jj are hoisted
+            // out of this loop and parked in local memory (4.6 KB of spills)
+            asm volatile("" ::: "memory");
+            double x[SB];
+            double* gX = A + size_t(r0) * lda + row;
+#pragma unroll
+            for (int c = 0; c < SB; ++c) x[c] = gX[size_t(c) * lda];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                const double xc = x[c] * invd[c];
+                x[c] = xc;
+                const double* lc = Lcm + c * BL_LP;
+                if (((c + 1) & 1) != 0 && c + 1 < SB) x[c + 1] = fma(-xc, lc[c + 1], x[c + 1]);
+#pragma unroll
+                for (int jj = (c + 2) & ~1; jj < SB; jj += 2) {
+                    const double2 l2 = *reinterpret_cast<const double2*>(lc + jj);
+                    x[jj] = fma(-xc, l2.x, x[jj]);
+                    x[jj + 1] = fma(-xc, l2.y, x[jj + 1]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < SB; ++c) gX[size_t(c) * lda] = x[c];
+        }
+        // the next block column's TMA reads (async proxy) must see these generic-proxy writes
+        asm volatile("fence.proxy.async;" ::: "memory");
         __syncthreads();
     }
     if (tid == 0) d_info[blockIdx.x] = s_info;

@@ -25,6 +25,8 @@ namespace {
 std::mutex g_mu;
 bool g_force_wide = false;  // CHOL_GEMM_WIDE=1: use the 128x128 shape everywhere (A/B experiments)
 bool g_inited[64] = {false};
+int g_batched_ll = 4;       // CHOL_BATCHED_LL: 4 = left-looking DMMA kernel, 4 stages x 4 CTAs/SM (default);
+                            // 6 = 6 stages x 3 CTAs/SM; 0 = round-1 kernels (A/B experiments)
 
 }  // namespace
 
@@ -56,6 +58,17 @@ int ensure_init() {
     e = cudaFuncSetAttribute(potrf_batched_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(batched_global_smem(BATCHED_MAX_N)));
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_batched_global_kernel)");
+    e = cudaFuncSetAttribute(potrf_batched_ll_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(BatchedLL<4>::SMEM));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_batched_ll_kernel<4,4>)");
+    e = cudaFuncSetAttribute(potrf_batched_ll_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(BatchedLL<6>::SMEM));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_batched_ll_kernel<6,3>)");
+    cudaFuncSetAttribute(potrf_batched_ll_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(potrf_batched_ll_kernel<6, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    if (const char* w = getenv("CHOL_BATCHED_LL")) g_batched_ll = atoi(w);
     g_inited[dev] = true;
     return 0;
 }
@@ -315,6 +328,15 @@ int chol_potrf_batched(int n, int batch, double* A, int lda, long long stride, i
     if (!d_info) return fail_arg(6, "chol_potrf_batched", "d_info");
     if (int rc = ensure_init()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_batched_ll != 0 && n % BLW == 0 && n <= BATCHED_LL_MAX_N && lda % 2 == 0 && stride % 2 == 0 &&
+        aligned16(A)) {
+        if (g_batched_ll == 6)
+            potrf_batched_ll_kernel<6, 3><<<batch, BL_THREADS, BatchedLL<6>::SMEM, st>>>(n, A, lda, stride, d_info);
+        else
+            potrf_batched_ll_kernel<4, 4><<<batch, BL_THREADS, BatchedLL<4>::SMEM, st>>>(n, A, lda, stride, d_info);
+        CHECK_LAUNCH("potrf_batched_ll_kernel");
+        return 0;
+    }
     if (n <= NBD) {
         potrf_batched_smem_kernel<<<batch, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(n, A, lda, stride, d_info);
         CHECK_LAUNCH("potrf_batched_smem_kernel");
