@@ -34,6 +34,8 @@ from .tiles import TileMatrix
 
 class TiledCholesky:
     """Plan + executor for the in-place factorization of a TileMatrix (lower, A = L L^T)."""
+    trace = None
+    tr = None
 
     def __init__(self, A: TileMatrix, group=None, lookahead: bool = True):
         self.A = A
@@ -81,6 +83,7 @@ class TiledCholesky:
             # same order everywhere, never lazily inside the factorization
             self._make_column_groups()
         self.update_events = None   # set to [] to time every trailing-update launch (bench.py roofline)
+        self.trace = None           # set to [] to record a CUDA-event timeline of the next pass (tools/)
         self._build_plan()
         if self.cuda:
             self.s_update = torch.cuda.Stream(self.dev)
@@ -286,7 +289,9 @@ class TiledCholesky:
         in_col = kq == lay.q
         is_diag = in_col and kp == lay.p
         if is_diag:
+            self._mark("potrf0", k, self.s_panel)
             self._k_potrf(self.A.tile_ptr(k, k), k * self.b, st)
+            self._mark("potrf1", k, self.s_panel)
         self._l_ptr = self.A.tile_ptr(k, k) if is_diag else 0
         self._w_ptr = self.work.data_ptr()
         if g.P > 1 and in_col and k + 1 < nt:
@@ -295,6 +300,7 @@ class TiledCholesky:
                     self.tr.send_diag(k, self._l_ptr, self._w_ptr, st, self._send_stream_of)
                 elif self.rank in self.tr.diag_readers(k):
                     self.tr.wait_diag(k, st)
+                    self._mark("diag_in", k, self.s_panel)
                     self._l_ptr, self._w_ptr = self.tr.diag_tile_ptr(k), self.tr.diag_work_ptr(k)
                 return
             cg = self._column_group(kq)
@@ -313,7 +319,9 @@ class TiledCholesky:
         if factor:
             toff, cnt = self.step_trsm[k]
             if cnt:
+                self._mark("trsm0", k, self.s_panel)
                 self._k_trsm_panel(self._l_ptr, self._w_ptr, self.d_trsm_ptrs.data_ptr() + toff * 8, cnt, st)
+                self._mark("trsm1", k, self.s_panel)
         if self.world > 1 and k + 1 < nt:
             if self.tr is not None:
                 if kq == lay.q:
@@ -321,6 +329,7 @@ class TiledCholesky:
                     if len(rows):
                         self.tr.send_panel(k, self.A.tile_ptr(rows[0], k), st, self._send_stream_of)
                 self.tr.wait_panel(k, st)
+                self._mark("panel_in", k, self.s_panel)
                 return
             _, groups = panel_slots(nt, g.P, k)
             for p, first, cnt in groups:
@@ -404,6 +413,7 @@ class TiledCholesky:
                 # A rank that owns nothing of a stage has nothing to wait for: it only receives, and may
                 # join the broadcasts as soon as its receive slot is free (ev_upd of step k-1).
                 ev_diag = ev_col = None
+                self._mark("upd0", k, self.s_update)
                 if nd:
                     self._k_update(base, nd, st)
                     ev_diag = self._record()
@@ -411,6 +421,7 @@ class TiledCholesky:
                     self._k_update(base + nd * 32, na - nd, st)
                 if na:
                     ev_col = self._record()
+                    self._mark("upd_a", k, self.s_update)
                 if gated:
                     # host-resident input: release part b group by group behind the upload
                     for g, (t0, t1, _, _) in enumerate(self.step0_groups):
@@ -419,6 +430,7 @@ class TiledCholesky:
                 elif ntot > na:
                     self._k_update(base + na * 32, ntot - na, st)
                 ev_upd[k % ns] = self._record()
+                self._mark("upd1", k, self.s_update)
                 self._release_panel(k, ev_upd[k % ns])
         if cuda:
             cur.wait_stream(self.s_update)
@@ -430,6 +442,19 @@ class TiledCholesky:
                 tr.end_run(cur.cuda_stream)
         elif tr is not None:
             tr.end_run(0)
+
+    def _mark(self, name: str, k: int, stream) -> None:
+        """Timeline marker (only when self.trace is a list): a timing event on `stream`."""
+        if self.trace is not None and self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.trace.append((name, k, ev))
+
+    def trace_ms(self) -> list:
+        """[(name, k, milliseconds since the first marker)] of the traced pass; synchronises."""
+        torch.cuda.synchronize(self.dev)
+        t0 = self.trace[0][2]
+        return [(n, k, t0.elapsed_time(ev)) for n, k, ev in self.trace]
 
     def _release_panel(self, k: int, ev) -> None:
         """Update k is enqueued (event `ev`): tell the owners that panel slot k % nslots is free."""

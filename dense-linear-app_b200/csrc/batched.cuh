@@ -125,9 +125,22 @@ struct BatchedLL {
     static constexpr size_t SMEM = size_t(STAGES * SLAB + BLW * BL_LP + BLW) * 8 + 2 * STAGES * 8 + 16;
 };
 
+// 1/sqrt(d) for a positive normal double: the hardware's 23-bit seed (MUFU.RSQ64H) refined by two
+// Newton steps, all inline — the library rsqrt() carries a slow path whose call spills the 32 row
+// registers of the factorization around every pivot.  ~1 ulp.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double h = 0.5 * d;
+    double e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-h * r, r, 0.5);
+    return fma(r, e, r);
+}
+
 // In-register Cholesky of a 32x32 block, lane = row (a[j] = element (lane, j), upper part ignored).
-// Pivot through rsqrt: piv = d * rsqrt(d), 1/piv = rsqrt(d) — one special-function sequence instead of
-// a square root and a division on the dependent chain.  Returns the 1-based index of the first
+// Pivot through rsqrt_pos: 1/piv = rsqrt(d) feeds the column scaling, piv = d * rsqrt(d) (+ one
+// correction) only the diagonal — no square root and no division on the dependent chain.  Returns the 1-based index of the first
 // non-positive (or NaN) pivot, 0 if none; inv_out = 1 / l_cc of this lane's own diagonal element.
 __device__ __forceinline__ int potrf32_regs(double (&a)[SB], double& inv_out) {
     const int lane = threadIdx.x & 31;
@@ -137,8 +150,9 @@ __device__ __forceinline__ int potrf32_regs(double (&a)[SB], double& inv_out) {
     for (int c = 0; c < SB; ++c) {
         const double d = __shfl_sync(0xffffffffu, a[c], c);
         if (!(d > 0.0) && info == 0) info = c + 1;
-        const double inv = rsqrt(d);
-        const double piv = d * inv;
+        const double inv = rsqrt_pos(d);
+        double piv = d * inv;
+        piv = fma(fma(-piv, piv, d), 0.5 * inv, piv);     // off the dependent chain: sqrt(d) to < 1 ulp
         const double l = (lane == c) ? piv : a[c] * inv;
         a[c] = l;
         if (lane == c) inv_out = inv;

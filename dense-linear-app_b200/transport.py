@@ -99,6 +99,7 @@ class PeerTransport:
         self.off_panel = self.off_diag + self.NDIAG * self.diag_stride
         self.nbytes = self.off_panel + self.nslots * self.slot_tiles * self.tile_bytes
         assert 4 * self.world * 4 <= FLAG_BYTES
+        self._plan_cache, self._diag_cache = {}, {}
         self.epoch = 0
         self.base = 0
         self.local = 0            # address of this rank's buffer
@@ -139,9 +140,11 @@ class PeerTransport:
     # ---- L_kk down the process column --------------------------------------------------------------
     def diag_readers(self, k: int) -> list[int]:
         """Ranks (other than the diagonal owner) of process column k % Q that own tiles of panel k."""
-        g = self.grid
-        _, groups = panel_slots(self.nt, g.P, k)
-        return [g.rank_of(p, k % g.Q) for p, _, cnt in groups if cnt and p != k % g.P]
+        if k not in self._diag_cache:
+            g = self.grid
+            _, groups = panel_slots(self.nt, g.P, k)
+            self._diag_cache[k] = [g.rank_of(p, k % g.Q) for p, _, cnt in groups if cnt and p != k % g.P]
+        return self._diag_cache[k]
 
     def send_diag(self, k: int, l_ptr: int, work_ptr: int, ready_stream, send_stream_of) -> None:
         Q, tb = self.grid.Q, self.tile_bytes
@@ -170,9 +173,11 @@ class PeerTransport:
     # ---- the factored panel ------------------------------------------------------------------------
     def panel_plan(self, k: int):
         """[(owner rank, po, first_slot, {reader rank: [(t0, count, stride)]})] for panel k."""
+        if k in self._plan_cache:
+            return self._plan_cache[k]
         g, nt = self.grid, self.nt
         _, groups = panel_slots(nt, g.P, k)
-        out = []
+        out = self._plan_cache[k] = []
         for po, first, cnt in groups:
             if not cnt:
                 continue

@@ -117,7 +117,8 @@ def test_config2_properties_full_size(cuda_lib):
     assert res["fro"] <= 1e-13 and res["inf"] <= 1e-13
 
 
-@pytest.mark.parametrize("n,batch", [(1, 3), (5, 7), (32, 64), (128, 33), (200, 5), (256, 40)])
+@pytest.mark.parametrize("n,batch", [(1, 3), (5, 7), (32, 64), (64, 20), (96, 11), (128, 33), (160, 9), (200, 5),
+                                     (224, 6), (256, 40), (256, 700), (288, 4)])
 def test_potrf_batched(cuda_lib, oracle, n, batch):
     """configs[4] shape (many small SPD matrices, n=256) at a test-sized batch."""
     from dense_linear_app_b200 import tile_ops
@@ -136,6 +137,56 @@ def test_potrf_batched(cuda_lib, oracle, n, batch):
             got = out[i].T
             assert np.abs(np.tril(got) - np.tril(ref)).max() <= 1e-13 * np.abs(ref).max()
             assert np.array_equal(np.triu(got, 1), np.triu(m, 1))
+
+
+@pytest.mark.parametrize("n,lda,pad", [(256, 258, 6), (96, 96, 0), (64, 65, 1), (128, 130, 2)])
+def test_potrf_batched_strided_through_the_c_abi(cuda_lib, oracle, n, lda, pad):
+    """lda > n and a padded matrix stride: even lda/stride take the left-looking DMMA kernel, odd ones
+    the generic kernels; rows n..lda-1 and the padding must come back untouched."""
+    batch = 7
+    stride = lda * n + pad
+    host = np.full(batch * stride, -7.5)
+    mats = []
+    for i in range(batch):
+        m = oracle.plgsy(float(n), n, 100 + i)
+        mats.append(m)
+        blk = host[i * stride:i * stride + lda * n].reshape(n, lda)      # [col, row]
+        blk[:, :n] = m.T
+    d = torch.from_numpy(host.copy()).cuda()
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    cuda_lib.call("chol_potrf_batched", n, batch, d.data_ptr(), lda, stride, info.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream)
+    out = d.cpu().numpy()
+    assert not info.cpu().numpy().any()
+    for i, m in enumerate(mats):
+        ref = m.copy(order="F")
+        assert oracle.potrf_tile(ref) == 0
+        blk = out[i * stride:i * stride + lda * n].reshape(n, lda)
+        got = blk[:, :n].T
+        assert np.abs(np.tril(got) - np.tril(ref)).max() <= 1e-13 * np.abs(ref).max()
+        assert np.array_equal(np.triu(got, 1), np.triu(m, 1))
+        assert np.all(blk[:, n:] == -7.5)
+        assert np.all(out[i * stride + lda * n:(i + 1) * stride] == -7.5)
+
+
+def test_potrf_batched_config4_full_size_properties(cuda_lib):
+    """BASELINE configs[4] at its full size (10 000 x 256): info == 0 everywhere and the backward
+    error ||A - L L^T||_F / ||A||_F of EVERY matrix <= 1e-13 (checked with torch.bmm, the checker)."""
+    from dense_linear_app_b200 import tile_ops
+    batch, n = 10000, 256
+    st = torch.cuda.current_stream().cuda_stream
+    A = torch.empty(batch, n, n, dtype=torch.float64, device="cuda")
+    for i in range(batch):
+        cuda_lib.call("chol_plgsy_tile", float(n), n, n, A[i].data_ptr(), n, n, 0, 0, n, 42 + i, st)
+    A0 = A.clone()
+    info = tile_ops.potrf_batched(A)
+    assert int((info != 0).sum().item()) == 0
+    Lt = torch.triu(A)                      # torch sees the transpose: upper == L^T
+    full = torch.triu(A0) + torch.triu(A0, 1).transpose(1, 2)
+    R = full - Lt.transpose(1, 2) @ Lt
+    err = torch.linalg.matrix_norm(R) / torch.linalg.matrix_norm(full)
+    assert float(err.max().item()) <= 1e-13
+    assert torch.equal(torch.tril(A, -1), torch.tril(A0, -1))      # strict upper (col-major) untouched
 
 
 def test_worker_execute_runs_the_client_dag(cuda_lib, oracle):
