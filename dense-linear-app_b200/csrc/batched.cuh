@@ -156,10 +156,17 @@ __device__ __forceinline__ int potrf32_regs(double (&a)[SB], double& inv_out) {
         const double l = (lane == c) ? piv : a[c] * inv;
         a[c] = l;
         if (lane == c) inv_out = inv;
+        // the broadcasts of l_jc are issued eight at a time ahead of the FMAs that use them: a shuffle
+        // directly in front of its FMA exposes the full shuffle latency 496 times (ncu: 12 us per block)
 #pragma unroll
-        for (int j = c + 1; j < SB; ++j) {
-            const double ljc = __shfl_sync(0xffffffffu, l, j);
-            a[j] = fma(-l, ljc, a[j]);
+        for (int j0 = c + 1; j0 < SB; j0 += 8) {
+            double lj[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (j0 + u < SB) lj[u] = __shfl_sync(0xffffffffu, l, j0 + u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (j0 + u < SB) a[j0 + u] = fma(-l, lj[u], a[j0 + u]);
         }
     }
     return info;
@@ -198,10 +205,19 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
         const int r0 = j * BLW;
         const int R = n - r0;
         const int nslab = r0 / BLK;                 // K = 32 j columns of L to the left
-        if (nslab > 0) {
-            for (int pass = 0; pass < 2; ++pass) {
+        if (warp == BL_CONSUMERS) {
+            // warm L2 with the part of the matrix the next steps read from HBM: block column j + 1
+            // (and, at the start, block column 0), so the epilogue / potrf / trsm loads hit L2
+            if (j == 0) bulk_prefetch_l2(A + size_t(lane) * lda + lane / 2 * 2, uint32_t(n - lane / 2 * 2) * 8u);
+            const int cn = r0 + BLW + lane;
+            if (cn < n) bulk_prefetch_l2(A + size_t(cn) * lda + r0 + BLW, uint32_t(n - r0 - BLW) * 8u);
+        }
+        // one update pass: rows [row_first, row_first + prow) of block column j.  Pass 0 is run by
+        // every warp; pass 1 (rows beyond the first 128) by warps 1..3 and the producer only — warp 0
+        // factors the diagonal block meanwhile, and warp 1 releases the slabs on its behalf.
+        auto run_pass = [&](const int pass) {
+            {
                 const int prow = pass == 0 ? min(R, BL_ROWS) : R - BL_ROWS;   // rows of C in this pass
-                if (prow <= 0) break;
                 const int row_first = pass == 0 ? r0 : r0 + BL_ROWS;
                 if (warp == BL_CONSUMERS) {
                     // ---------------- producer: slab = [32 B-rows | the pass' own rows] x 8 columns
@@ -231,15 +247,34 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
                     const int blk = pass == 0 ? warp : warp - 1;
                     const bool has = blk >= 0 && blk * BLW < prow;
                     const int slab_row = pass == 0 ? blk * BLW : BLW + blk * BLW;
+                    // the accumulators start as the block of A itself (its HBM latency hides behind the
+                    // first slab's) and the products are subtracted by negating the B fragments
                     double acc[2][2][2][2][2];
+                    double* gC = A + size_t(r0) * lda + row_first + blk * BLW;
+                    if (has) {
 #pragma unroll
-                    for (int q = 0; q < 2; ++q)
+                        for (int q = 0; q < 2; ++q)
 #pragma unroll
-                        for (int r = 0; r < 2; ++r)
+                            for (int r = 0; r < 2; ++r)
 #pragma unroll
-                            for (int mp = 0; mp < 2; ++mp)
+                                for (int e = 0; e < 2; ++e)
 #pragma unroll
-                                for (int np = 0; np < 2; ++np) acc[q][r][mp][np][0] = acc[q][r][mp][np][1] = 0.0;
+                                    for (int np = 0; np < 2; ++np) {
+                                        const double2 v = *reinterpret_cast<const double2*>(
+                                            gC + size_t(r * 16 + 4 * t + 2 * e + np) * lda + q * 16 + 2 * g);
+                                        acc[q][r][0][np][e] = v.x;
+                                        acc[q][r][1][np][e] = v.y;
+                                    }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+#pragma unroll
+                            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                                    for (int np = 0; np < 2; ++np) acc[q][r][0][np][e] = acc[q][r][1][np][e] = 0.0;
+                    }
                     for (int s = 0; s < nslab; ++s, ++it) {
                         const int st = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
@@ -253,8 +288,11 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
                                 for (int q = 0; q < 2; ++q)
                                     a[q] = *reinterpret_cast<const double2*>(sl + kk * BL_PITCH + slab_row + q * 16);
 #pragma unroll
-                                for (int r = 0; r < 2; ++r)
+                                for (int r = 0; r < 2; ++r) {
                                     b[r] = *reinterpret_cast<const double2*>(sl + kk * BL_PITCH + r * 16);
+                                    b[r].x = -b[r].x;
+                                    b[r].y = -b[r].y;
+                                }
 #pragma unroll
                                 for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -267,13 +305,19 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
                             }
                         }
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + st]));
+                        if (lane == 0) {
+                            mbar_arrive(smem_u32(&bars[STAGES + st]));
+                            if (pass == 1 && warp == 1) mbar_arrive(smem_u32(&bars[STAGES + st]));   // for warp 0
+                        }
                     }
                     if (has) {
-                        // C = A - acc, 2 consecutive rows per access; the diagonal block keeps its
-                        // strict upper triangle untouched
+                        // 2 consecutive rows per access; the diagonal block keeps its strict upper
+                        // triangle untouched
                         const bool diag = pass == 0 && blk == 0;
-                        double* gC = A + size_t(r0) * lda + row_first + blk * BLW;
+                        // (opaque copy of the base: keeps the 16 store addresses from being computed
+                        // before the main loop and carried through it in registers -> spills)
+                        double* gS = gC;
+                        asm volatile("" : "+l"(gS));
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -284,23 +328,28 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
                                     for (int np = 0; np < 2; ++np) {
                                         const int rl = q * 16 + 2 * g;
                                         const int cl = r * 16 + 4 * t + 2 * e + np;
-                                        double* ptr = gC + size_t(cl) * lda + rl;
+                                        double* ptr = gS + size_t(cl) * lda + rl;
                                         if (diag && rl < cl) {
-                                            if (rl + 1 == cl) ptr[1] -= acc[q][r][1][np][e];
+                                            if (rl + 1 == cl) ptr[1] = acc[q][r][1][np][e];
                                             continue;
                                         }
-                                        double2 v = *reinterpret_cast<const double2*>(ptr);
-                                        v.x -= acc[q][r][0][np][e];
-                                        v.y -= acc[q][r][1][np][e];
-                                        *reinterpret_cast<double2*>(ptr) = v;
+                                        *reinterpret_cast<double2*>(ptr) =
+                                            make_double2(acc[q][r][0][np][e], acc[q][r][1][np][e]);
                                     }
                     }
                 }
             }
-            __syncthreads();    // the updated block column is visible to the whole CTA
+        };
+        const bool two = nslab > 0 && R > BL_ROWS;
+        if (nslab > 0) {
+            run_pass(0);
+            __syncthreads();    // the updated diagonal block (pass 0, block 0) is visible to warp 0
         }
-        // ---- diagonal block: one warp, registers + shuffles
-        if (warp == 0) {
+        // ---- diagonal block: one warp, registers + shuffles; the others finish the update meanwhile
+        if (warp != 0) {
+            if (two) run_pass(1);
+        } else {
+            if (two) it += nslab;
             double a[SB];
             const double* gD = A + size_t(r0) * lda + r0 + lane;
 #pragma unroll

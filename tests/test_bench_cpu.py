@@ -17,8 +17,22 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["metric"] == "fp64_cholesky_tflops" and d["unit"] == "TFLOP/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["dtype"] == "f64"
     assert d["config"]["N"] == 65536 and d["config"]["tile"] == 1024
+    # the arm says which bounded sample it really timed (the reference program's N is fixed in its source)
+    assert d["config"]["N_timed"] == 12000 and "BOUNDED SAMPLE" in d["config"]["workload"]
+    assert d["tiled_single_worker"]["info"] == 0 and d["tiled_single_worker"]["backward_error"] <= 1e-13
+    assert d["monolithic_N16384_all_cores"]["info"] == 0 and d["monolithic_N16384_all_cores"]["tflops"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_batched_leg():
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "batched",
+                         "--steps", "1", "--warmup", "0", "--batch", "300"], capture_output=True, text=True,
+                        timeout=600, cwd=ROOT)
+    assert pr.returncode == 0, pr.stderr[-2000:]
+    d = json.loads([l for l in pr.stdout.splitlines() if l.strip()][-1])
+    assert d["impl"] == "reference" and d["metric"] == "fp64_batched_cholesky_tflops" and d["value"] > 0
+    assert d["config"]["n"] == 256 and d["cpu_baseline"]["cores"] == 1
 
 
 def test_reference_arm_other_ranks_exit_quietly():
