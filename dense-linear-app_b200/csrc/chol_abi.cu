@@ -11,6 +11,7 @@
 #include "batched.cuh"
 #include "gemm_dmma.cuh"
 #include "panel.cuh"
+#include "panel2.cuh"
 
 using namespace chol;
 
@@ -25,6 +26,7 @@ namespace {
 std::mutex g_mu;
 bool g_force_wide = false;  // CHOL_GEMM_WIDE=1: use the 128x128 shape everywhere (A/B experiments)
 bool g_inited[64] = {false};
+bool g_panel_v1 = false;    // CHOL_PANEL_V1=1: round-1 panel kernels (full 128x128 inverses) for every tile size
 int g_batched_ll = 4;       // CHOL_BATCHED_LL: 4 = left-looking DMMA kernel, 4 stages x 4 CTAs/SM (default);
                             // 6 = 6 stages x 3 CTAs/SM; 0 = round-1 kernels (A/B experiments)
 
@@ -69,6 +71,13 @@ int ensure_init() {
     cudaFuncSetAttribute(potrf_batched_ll_kernel<6, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     if (const char* w = getenv("CHOL_BATCHED_LL")) g_batched_ll = atoi(w);
+    if (const char* w = getenv("CHOL_PANEL_V1")) g_panel_v1 = (w[0] == '1');
+    e = cudaFuncSetAttribute(potrf_diag32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(D2_SMEM));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_diag32_kernel)");
+    e = cudaFuncSetAttribute(trsm_leaf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LF_SMEM));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(trsm_leaf32_kernel)");
+    cudaFuncSetAttribute(potrf_diag32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(trsm_leaf32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     g_inited[dev] = true;
     return 0;
 }
@@ -140,6 +149,28 @@ int launch_one(const chol_task_t& t, int m, int n, int k, int lda, int ldb, int 
     return launch_gemm(p, st, inplace_tri);
 }
 
+// Tiles whose size is a multiple of 32 take the second-generation panel kernels (panel2.cuh).
+inline bool fast32(int b, int lda, int ldl, const void* a, const void* l) {
+    return !g_panel_v1 && b % SB == 0 && lda % 2 == 0 && ldl % 2 == 0 && aligned16(a) && aligned16(l);
+}
+
+// X = A L_jj^{-T} on the 128-column block at `off` of one matrix (`single`) or of every tile of a
+// pointer list: m rows, nbv (multiple of 32) columns.
+int launch_leaf(double* const* d_tiles, double* single, int ntiles, long long off, int m, int nbv, int lda,
+                const double* Ljj, int ldl, const double* Dinv, cudaStream_t st) {
+    if (ntiles <= 0 || m <= 0 || nbv <= 0) return 0;
+    LeafParams p;
+    p.tile_ptrs = d_tiles; p.single = single; p.off = off;
+    p.m = m; p.nbk = nbv / SB; p.lda = lda;
+    p.L = Ljj; p.ldl = ldl; p.Dinv = Dinv;
+    p.ctas_per_task = (m + LF_ROWS - 1) / LF_ROWS;
+    const long long grid = (long long)ntiles * p.ctas_per_task;
+    if (grid > 0x7fffffffLL) return fail_arg(6, "chol_trsm_tiles", "too many CTAs");
+    trsm_leaf32_kernel<<<dim3((unsigned)grid), LF_THREADS, LF_SMEM, st>>>(p);
+    CHECK_LAUNCH("trsm_leaf32_kernel");
+    return 0;
+}
+
 // X * L^T = A for one tile (`single`) or every tile of a panel (`d_tiles`), recursively over the
 // 128-column blocks [lo, hi) of L:   solve(lo, mid);  A[:, mid:hi) -= X[:, lo:mid) L[mid:hi, lo:mid)^T;
 // solve(mid, hi);   a leaf multiplies by the inverted diagonal block: X_j = A_j inv(L_jj)^T.
@@ -154,6 +185,7 @@ struct TrsmCtx {
     double* single;
     int ntiles, lda;
     cudaStream_t st;
+    bool v2;        // leaves by block substitution with the 32x32 inverses (trsm_leaf32_kernel)
 };
 
 int trsm_issue(const TrsmCtx& c, long long c_off, long long a_off, const double* B, int n, int k, int ldb,
@@ -171,6 +203,9 @@ int trsm_rec(const TrsmCtx& c, int lo, int hi) {
     if (hi - lo == 1) {
         const int o = lo * NBD;
         const int nbv = (c.b - o < NBD) ? c.b - o : NBD;
+        if (c.v2)
+            return launch_leaf(c.d_tiles, c.single, c.ntiles, (long long)o * c.lda, c.b, nbv, c.lda,
+                               c.L + size_t(o) * c.ldl + o, c.ldl, c.Winv + size_t(lo) * NBD * NBD, c.st);
         return trsm_issue(c, (long long)o * c.lda, (long long)o * c.lda, c.Winv + size_t(lo) * NBD * NBD, nbv, nbv, NBD,
                           1.0, 0.0, true);
     }
@@ -186,7 +221,9 @@ int trsm_rec(const TrsmCtx& c, int lo, int hi) {
 
 int trsm_sweep(int b, const double* L, int ldl, const double* Winv, double* const* d_tiles, double* single,
                int ntiles, int lda, cudaStream_t st) {
-    TrsmCtx c{b, L, ldl, Winv, d_tiles, single, ntiles, lda, st};
+    // (the tiles of a pointer list are 16-byte aligned by contract, see chol_b200.h)
+    const bool v2 = fast32(b, lda, ldl, single ? (const void*)single : (const void*)L, L) && aligned16(Winv);
+    TrsmCtx c{b, L, ldl, Winv, d_tiles, single, ntiles, lda, st, v2};
     return trsm_rec(c, 0, (b + NBD - 1) / NBD);
 }
 
@@ -234,19 +271,30 @@ int chol_potrf_tile(int b, double* A, int lda, double* work, int* d_info, int in
     if (int rc = ensure_init()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = (b + NBD - 1) / NBD;
+    const bool v2 = fast32(b, lda, lda, A, A) && aligned16(work);
     for (int j = 0; j < nblk; ++j) {
         const int o = j * NBD;
         const int nbv = (b - o < NBD) ? b - o : NBD;
         const int rem = b - o - nbv;
         double* Wj = work + size_t(j) * NBD * NBD;
         double* Ajj = A + size_t(o) * lda + o;
-        potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(nbv, Ajj, lda, Wj, d_info, info_base + o);
-        CHECK_LAUNCH("potrf_diag_kernel");
+        if (v2) {
+            potrf_diag32_kernel<<<1, D2_THREADS, D2_SMEM, st>>>(nbv, Ajj, lda, Wj, d_info, info_base + o);
+            CHECK_LAUNCH("potrf_diag32_kernel");
+        } else {
+            potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(nbv, Ajj, lda, Wj, d_info, info_base + o);
+            CHECK_LAUNCH("potrf_diag_kernel");
+        }
         if (rem > 0) {
             chol_task_t t;
             // rows below the diagonal block: X = A * inv(L_jj)^T (in place; each CTA owns its rows)
-            t.C = Ajj + nbv; t.A = t.C; t.B = Wj; t.flags = 0;
-            int rc = launch_one(t, rem, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
+            int rc;
+            if (v2) {
+                rc = launch_leaf(nullptr, Ajj + nbv, 1, 0, rem, nbv, lda, Ajj, lda, Wj, st);
+            } else {
+                t.C = Ajj + nbv; t.A = t.C; t.B = Wj; t.flags = 0;
+                rc = launch_one(t, rem, nbv, nbv, lda, NBD, lda, 1.0, 0.0, st, true);
+            }
             if (rc) return rc;
             // trailing lower triangle: A22 -= X * X^T
             t.C = A + size_t(o + nbv) * lda + (o + nbv); t.A = Ajj + nbv; t.B = t.A; t.flags = CHOL_TASK_LOWER;

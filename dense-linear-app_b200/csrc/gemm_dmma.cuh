@@ -25,8 +25,8 @@
 //   * one LDS.128 feeds two DMMAs (even/odd rows), so a k4 step is 6 LDS.128 : 32 DMMA;
 //   * C is read-modify-written straight from the accumulators: each lane owns 2x4
 //     patches (2 consecutive rows x 4 consecutive columns) -> 16-byte accesses, every
-//     warp-wide access covers four full 128-byte lines; the producer prefetches the C
-//     block into L2 while the main loop runs.
+//     warp-wide access covers four full 128-byte lines; the loads of a 16-row group are issued
+//     together, and the producer prefetches the C block into L2 while the main loop runs.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
         const double* gB = task.B + col0;
         if (p.beta != 0.0) {
             // warm L2 with this block of C for the epilogue
-            const double* gC = task.C + size_t(col0) * p.ldc + row0;
-            for (int c = lane; c < nv; c += 32) bulk_prefetch_l2(gC + size_t(c) * p.ldc, uint32_t(mv) * 8u);
+            const double* gCp = task.C + size_t(col0) * p.ldc + row0;
+            for (int c = lane; c < nv; c += 32) bulk_prefetch_l2(gCp + size_t(c) * p.ldc, uint32_t(mv) * 8u);
         }
         const bool isA = lane < BK;
         const int col = isA ? lane : lane - BK;
@@ -260,6 +260,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
     }
 
     // ================================ epilogue ========================================
+    // C <- beta*C + alpha*acc.  The products are summed on their own (from zero) and C enters once at the
+    // end: starting the accumulators at C would save the loads below but rounds every one of the K FMAs at
+    // the magnitude of C — measured: backward error 3e-15 instead of 4e-16 on the diagonally dominant test
+    // matrices.  The eight 16-byte loads of a 16-row group are issued together (the previous one-at-a-time
+    // read-modify-write paid 32 dependent round trips per thread: 18 us of a 29 us K = 128 launch); the
+    // producer warmed L2 with this block of C while the main loop ran.
     const double alpha = p.alpha, beta = p.beta;
     const bool diag_block = lower && (col0 + BN > row0);   // block touches the diagonal
     double* gC = task.C + size_t(col0) * p.ldc + row0;
@@ -267,8 +273,24 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
     for (int q = 0; q < 4; ++q) {
         const int r_loc = wm * 64 + q * 16 + 2 * g;  // first of the two rows this lane owns
         if (r_loc >= mv) continue;                   // mv is even: the pair is in or out together
+        double2 old[2][2][2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    const int c_loc = wn * 32 + r * 16 + 4 * t + 2 * e + np;
+                    old[r][e][np] = make_double2(0.0, 0.0);
+                    if (beta == 0.0 || c_loc >= nv) continue;
+                    const double* ptr = gC + size_t(c_loc) * p.ldc + r_loc;
+                    if (!diag_block || row0 + r_loc >= col0 + c_loc)
+                        old[r][e][np] = *reinterpret_cast<const double2*>(ptr);
+                    else if (row0 + r_loc + 1 == col0 + c_loc)
+                        old[r][e][np].y = ptr[1];     // the pair straddles the diagonal: lower element only
+                }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
 #pragma unroll
@@ -278,22 +300,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
                     double* ptr = gC + size_t(c_loc) * p.ldc + r_loc;
                     double v0 = alpha * acc[q][r][0][np][e];
                     double v1 = alpha * acc[q][r][1][np][e];
+                    if (beta != 0.0) {
+                        v0 += beta * old[r][e][np].x;
+                        v1 += beta * old[r][e][np].y;
+                    }
                     if (diag_block && row0 + r_loc < col0 + c_loc) {
                         // pair straddles or lies above the diagonal
-                        if (row0 + r_loc + 1 == col0 + c_loc) {
-                            if (beta != 0.0) v1 += beta * ptr[1];
-                            ptr[1] = v1;
-                        }
+                        if (row0 + r_loc + 1 == col0 + c_loc) ptr[1] = v1;
                         continue;
-                    }
-                    if (beta != 0.0) {
-                        const double2 old = *reinterpret_cast<const double2*>(ptr);
-                        v0 += beta * old.x;
-                        v1 += beta * old.y;
                     }
                     *reinterpret_cast<double2*>(ptr) = make_double2(v0, v1);
                 }
-        }
     }
 }
 

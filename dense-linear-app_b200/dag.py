@@ -111,6 +111,68 @@ class MT19937_64:
         return (b - a) * c + a
 
 
+class NormalDist:
+    """std::normal_distribution<double>(0, 1) of libstdc++ on an MT19937_64: Marsaglia's polar method
+    over generate_canonical<double, 53> (one 64-bit word per canonical draw), the second value of
+    each accepted pair saved for the next call.  math.log / math.sqrt are libm's, as in the reference
+    binary, so the stream reproduces the C++ one bit for bit (tests/golden/normal_dist.json)."""
+
+    def __init__(self, gen: MT19937_64):
+        self.gen, self.saved = gen, None
+
+    def _canonical(self) -> float:
+        c = float(self.gen.raw(1)[0]) / 18446744073709551616.0
+        return c if c < 1.0 else float(np.nextafter(1.0, 0.0))
+
+    def __call__(self) -> float:
+        import math
+        if self.saved is not None:
+            v, self.saved = self.saved, None
+            return v
+        while True:
+            x = 2.0 * self._canonical() - 1.0
+            y = 2.0 * self._canonical() - 1.0
+            r2 = x * x + y * y
+            if not (r2 > 1.0 or r2 == 0.0):
+                break
+        mult = math.sqrt(-2.0 * math.log(r2) / r2)
+        self.saved = x * mult
+        return y * mult
+
+
+_v1_normal: NormalDist | None = None
+
+
+def generate_random_B_block(B: int, scale: float = 1.0, dist: NormalDist | None = None) -> np.ndarray:
+    """generate_random_B_block (C1:102-108): B*B draws of N(0, 1) * scale from ONE process-wide
+    mt19937_64(42) (the reference's generator is a function-level static, so consecutive calls
+    continue the same stream; pass `dist` to use a private stream).  Returned as the flat tile
+    blob the client uploads (B*B doubles; the worker reads it column-major, W1:212-227)."""
+    global _v1_normal
+    if dist is None:
+        if _v1_normal is None:
+            _v1_normal = NormalDist(MT19937_64(42))
+        dist = _v1_normal
+    return np.array([dist() * scale for _ in range(B * B)], dtype=np.float64)
+
+
+def make_blocks_v1(N: int, B: int, dist: NormalDist | None = None) -> dict:
+    """The v1 client's input (C1:189-192): every lower tile (i, j), i-major then j, is an independent
+    N(0, 0.1^2) block, diagonal tiles get +B on their diagonal.  Diagonal tiles are therefore NOT
+    symmetric: the factorization must read their lower triangle only (POTRF/SYRK uplo=Lower).
+    Returns {(i, j): flat blob}."""
+    dist = dist or NormalDist(MT19937_64(42))
+    nb = N // B
+    out = {}
+    for i in range(nb):
+        for j in range(i + 1):
+            blk = generate_random_B_block(B, 0.1, dist)
+            if i == j:
+                blk[np.arange(B) * B + np.arange(B)] += float(B)
+            out[(i, j)] = blk
+    return out
+
+
 def make_spd_like_chameleon(N: int, bump: float = 100.0, uplo: str = "L", seed: int = 12345) -> np.ndarray:
     """make_spd_like_chameleon (C2:224-252): lower triangle filled column by column with
     U(-0.5, 0.5) draws of mt19937_64(seed), mirrored, diagonal += bump.  Column-major N x N."""

@@ -15,6 +15,24 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def ill_conditioned_spd(n, cond, kind, seed=0):
+    """SPD test matrices far from cond ~ 1 (the generators of the reference only make those):
+    geo      Q diag(logspace(0, -log10 cond)) Q^T        geometrically spread spectrum
+    cluster  Q diag(1, ..., 1, 1/cond x n/8) Q^T           one small cluster
+    graded   D B D, B well conditioned, D = diag(logspace)   badly scaled rows/columns"""
+    rng = np.random.default_rng(seed)
+    if kind == "graded":
+        Bm = rng.standard_normal((n, n))
+        Bm = Bm @ Bm.T / n + np.eye(n)
+        s = np.logspace(0, -np.log10(cond) / 2, n)
+        A = (Bm * s).T * s
+    else:
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        d = np.logspace(0, -np.log10(cond), n) if kind == "geo" else np.where(np.arange(n) >= n - n // 8, 1.0 / cond, 1.0)
+        A = (Q * d) @ Q.T
+    return np.asfortranarray((A + A.T) / 2)
+
+
 def element_gate(L, Lref):
     floor = 1e-3 * np.abs(Lref).max()
     return np.all(np.abs(L - Lref) <= 1e-10 * np.maximum(np.abs(Lref), floor))
@@ -117,6 +135,83 @@ def test_config2_properties_full_size(cuda_lib):
     assert res["fro"] <= 1e-13 and res["inf"] <= 1e-13
 
 
+@pytest.mark.parametrize("kind", ["geo", "cluster", "graded"])
+@pytest.mark.parametrize("cond", [1e4, 1e8, 1e10])
+def test_factor_ill_conditioned_backward_error(cuda_lib, kind, cond):
+    """north_star limits the ELEMENT gate to well-conditioned inputs, not the backward-error gate:
+    ||A - L L^T||_F / ||A||_F <= 1e-13 must survive cond 1e4 ... 1e10 although TRSM and the POTRF panel
+    multiply by explicitly inverted 128 x 128 diagonal blocks."""
+    from scipy.linalg import lapack
+    from dense_linear_app_b200.cholesky import TiledCholesky
+    from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+    N, b = 2048, 512
+    A = ill_conditioned_spd(N, cond, kind)
+    M = TileMatrix(TileDesc.square(N, b)).from_numpy(A)
+    M0 = M.clone()
+    ch = TiledCholesky(M)
+    ch.factor()
+    assert ch.info() == 0
+    L = np.tril(M.to_numpy())
+    bwd = np.linalg.norm(L @ L.T - A) / np.linalg.norm(A)
+    Lref, info = lapack.dpotrf(A, lower=1, clean=1)
+    assert info == 0
+    bwd_ref = np.linalg.norm(Lref @ Lref.T - A) / np.linalg.norm(A)
+    assert bwd <= 1e-13, (bwd, bwd_ref)
+    assert bwd <= 50 * max(bwd_ref, 1e-16)             # and not qualitatively worse than LAPACK itself
+    assert ch.residual(M0)["fro"] <= 1e-13
+    # forward error scales with the condition number (as LAPACK's own does): only a sanity bound here
+    assert np.abs(L - Lref).max() <= 1e-14 * cond * np.abs(Lref).max()
+
+
+@pytest.mark.parametrize("b", [256, 1024])
+@pytest.mark.parametrize("cond", [1e6, 1e10])
+def test_tile_ops_ill_conditioned(cuda_lib, b, cond):
+    """POTRF and TRSM tile ops on an ill-conditioned tile: residuals ||A - L L^T|| and ||X L^T - B||
+    relative to the data stay at rounding level."""
+    from dense_linear_app_b200 import tile_ops
+    A = ill_conditioned_spd(b, cond, "geo", seed=3)
+    dA = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()
+    info = tile_ops.potrf_tile(dA)
+    assert int(info.item()) == 0
+    L = np.tril(dA.cpu().numpy().T)
+    assert np.linalg.norm(L @ L.T - A) / np.linalg.norm(A) <= 1e-13
+    rng = np.random.default_rng(5)
+    Bm = rng.standard_normal((b, b))
+    dB = torch.from_numpy(np.ascontiguousarray(Bm.T)).cuda()
+    tile_ops.trsm_tile(dA, dB)
+    X = dB.cpu().numpy().T
+    # normwise backward error of the solve X L^T = B
+    assert np.linalg.norm(X @ L.T - Bm) / (np.linalg.norm(X) * np.linalg.norm(L) + np.linalg.norm(Bm)) <= 1e-13
+
+
+def test_gpu_factor_matches_the_reference_programs_own_factor(cuda_lib, oracle):
+    """The one fixture that comes from the REFERENCE itself (tests/golden/ref_lapacke_dpotrf.json: output of
+    its lapacke_dpotrf.c, N=12000, compiled from /root/reference by oracle/Makefile): the GPU factors the
+    leading block of the same input (chol(A)[:m,:m] == chol(A[:m,:m])) and is compared with the recorded
+    entries directly, not through the oracle."""
+    import hashlib
+    from dense_linear_app_b200.cholesky import TiledCholesky
+    from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+    with open(os.path.join(ROOT, "tests", "golden", "ref_lapacke_dpotrf.json")) as f:
+        gold = json.load(f)
+    m = gold["m"]
+    A = np.asfortranarray(oracle.lp_matrix(gold["N"])[:m, :m])       # input generator only (sha-checked below)
+    assert hashlib.sha256(A.tobytes(order="F")).hexdigest() == gold["input_sha256_leading_block"]
+    for b in (256, 512):
+        M = TileMatrix(TileDesc.square(m, b)).from_numpy(A)
+        ch = TiledCholesky(M)
+        ch.factor()
+        assert ch.info() == 0
+        L = np.tril(M.to_numpy())
+        scale = np.abs(np.array(gold["diag"])).max()
+        got = L[np.array(gold["i"]), np.array(gold["j"])]
+        assert np.abs(got - np.array(gold["L"])).max() <= 1e-13 * scale
+        assert np.abs(np.diag(L) - np.array(gold["diag"])).max() <= 1e-13 * scale
+        ref = np.array(gold["L"])
+        floor = 1e-3 * scale
+        assert np.all(np.abs(got - ref) <= 1e-10 * np.maximum(np.abs(ref), floor))
+
+
 @pytest.mark.parametrize("n,batch", [(1, 3), (5, 7), (32, 64), (64, 20), (96, 11), (128, 33), (160, 9), (200, 5),
                                      (224, 6), (256, 40), (256, 700), (288, 4)])
 def test_potrf_batched(cuda_lib, oracle, n, batch):
@@ -207,6 +302,36 @@ def test_worker_execute_runs_the_client_dag(cuda_lib, oracle):
     ref = A.copy(order="F")
     assert oracle.potrf_tile(ref) == 0
     assert np.abs(L - np.tril(ref)).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_worker_runs_the_v1_client_input_with_nonsymmetric_diagonal_tiles(cuda_lib, oracle):
+    """v1 client input (C1:102-108,189-192): independent N(0, 0.1^2) tiles, +B on the diagonal tiles'
+    diagonal — the diagonal tiles are NOT symmetric, so this passes only if the GPU POTRF and SYRK read
+    and write the lower triangle alone.  Result == LAPACK factor of the implied symmetric matrix, and the
+    strict upper triangles of the diagonal tiles come back bit for bit."""
+    from dense_linear_app_b200 import dag, worker
+    N, B = 192, 64
+    blocks = dag.make_blocks_v1(N, B)
+    nb = N // B
+    A = np.zeros((N, N))
+    for (i, j), blob in blocks.items():
+        t = blob.reshape(B, B).T
+        A[i * B:(i + 1) * B, j * B:(j + 1) * B] = np.tril(t) if i == j else t
+    A = A + np.tril(A, -1).T
+    named = {dag.block_id_from_ij(i, j): v.tobytes() for (i, j), v in blocks.items()}
+    out = dag.run_waves(N, B, named, worker.execute)
+    L = np.zeros((N, N))
+    for i in range(nb):
+        for j in range(i + 1):
+            t = np.frombuffer(out[dag.block_id_from_ij(i, j)]).reshape(B, B).T
+            L[i * B:(i + 1) * B, j * B:(j + 1) * B] = t
+            if i == j:
+                assert np.array_equal(np.triu(t, 1), np.triu(blocks[(i, j)].reshape(B, B).T, 1))
+    L = np.tril(L)
+    ref = A.copy(order="F")
+    assert oracle.potrf_tile(ref) == 0
+    assert np.abs(L - np.tril(ref)).max() <= 1e-13 * np.abs(ref).max()
+    assert oracle.backward_error(np.asfortranarray(A), np.asfortranarray(L)) <= 1e-13
 
 
 def test_worker_error_statuses(cuda_lib):

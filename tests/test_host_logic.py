@@ -130,6 +130,62 @@ def test_mt19937_64_matches_libstdcxx_golden():
     assert int(dag.MT19937_64(42).raw(700)[-1]) == g["seed42_raw_700th"]
 
 
+def test_v1_normal_generator_matches_libstdcxx_golden():
+    """generate_random_B_block (C1:102-108): std::normal_distribution on mt19937_64(42), bit for bit."""
+    g = json.load(open(os.path.join(GOLD, "normal_dist.json")))
+    d = dag.NormalDist(dag.MT19937_64(g["seed"]))
+    v = [d() * g["scale"] for _ in range(2000)]
+    assert [float.fromhex(h) for h in g["first8_hex"]] == v[:8]
+    assert [float.fromhex(h) for h in g["last8_of_2000_hex"]] == v[-8:]
+    # the block helper continues ONE stream across calls, like the reference's function-level static
+    d2 = dag.NormalDist(dag.MT19937_64(42))
+    b0, b1 = dag.generate_random_B_block(4, 0.1, d2), dag.generate_random_B_block(4, 0.1, d2)
+    assert list(b0) == v[:16] and list(b1) == v[16:32]
+
+
+def v1_symmetric_matrix(blocks, N, B):
+    """The symmetric matrix the v1 tiles stand for: lower tiles as given, diagonal tiles' LOWER triangle."""
+    A = np.zeros((N, N))
+    for (i, j), blob in blocks.items():
+        t = blob.reshape(B, B).T          # the worker reads the blob column-major (W1:212-227)
+        A[i * B:(i + 1) * B, j * B:(j + 1) * B] = np.tril(t) if i == j else t
+    return A + np.tril(A, -1).T
+
+
+def test_v1_blocks_have_nonsymmetric_diagonal_tiles_and_factor_with_the_oracle(oracle):
+    """C1:189-192: N(0, 0.1^2) tiles, +B on the diagonal of diagonal tiles.  The diagonal tiles are not
+    symmetric — running the client DAG on them is the reference's own evidence that POTRF and SYRK read
+    the lower triangle only."""
+    N, B = 24, 8
+    blocks = dag.make_blocks_v1(N, B)
+    d00 = blocks[(0, 0)].reshape(B, B)
+    assert not np.allclose(d00, d00.T) and abs(d00[0, 0] - B) < 1.0
+    A = v1_symmetric_matrix(blocks, N, B)
+    named = {dag.block_id_from_ij(i, j): v.tobytes() for (i, j), v in blocks.items()}
+
+    def submit_one(payload, deps):
+        p = json.loads(payload)
+        t = lambda name: np.frombuffer(deps[p[name]]).reshape(B, B).T.copy(order="F")  # noqa: E731
+        if p["op"] == "POTRF":
+            a = t("in"); assert oracle.potrf_tile(a) == 0
+        elif p["op"] == "TRSM":
+            a = t("inA"); oracle.trsm_tile(t("inL"), a)
+        elif p["op"] == "SYRK":
+            a = t("inC"); oracle.syrk_tile(t("inA"), a)
+        else:
+            a = t("inC"); oracle.gemm_tile(t("inAi"), t("inAj"), a)
+        return a.tobytes(order="F")
+
+    out = dag.run_waves(N, B, named, submit_one)
+    nb = N // B
+    L = np.zeros((N, N))
+    for i in range(nb):
+        for j in range(i + 1):
+            L[i * B:(i + 1) * B, j * B:(j + 1) * B] = np.frombuffer(out[dag.block_id_from_ij(i, j)]).reshape(B, B).T
+    L = np.tril(L)
+    assert np.linalg.norm(L @ L.T - A) / np.linalg.norm(A) < 1e-15
+
+
 def test_make_spd_like_chameleon():
     N = 12
     A = dag.make_spd_like_chameleon(N)
