@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchol_b200.so")
+LIB_PATH = os.environ.get("CHOL_LIB_PATH") or os.path.join(_HERE, "libchol_b200.so")   # CHOL_LIB_PATH: A/B builds
 
 c_void_p, c_int, c_double, c_ll, c_ull, c_size_t = C.c_void_p, C.c_int, C.c_double, C.c_longlong, C.c_ulonglong, C.c_size_t
 
@@ -18,11 +18,14 @@ SIGNATURES = {
     "chol_version": (C.c_char_p, []),
     "chol_launch_count": (c_ull, []),
     "chol_gemm_tasks": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_void_p]),
+    "chol_gemm_tasks_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_int,
+                                   c_void_p]),
     "chol_potrf_tile_workspace": (c_size_t, [c_int]),
     "chol_potrf_tile": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "chol_trsm_tile_workspace": (c_size_t, [c_int]),
     "chol_trsm_tile": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "chol_trsm_tiles": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "chol_trsm_tiles_push": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "chol_syrk_tile": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "chol_gemm_tile": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "chol_potrf_batched": (c_int, [c_int, c_int, c_void_p, c_int, c_ll, c_void_p, c_void_p]),

@@ -40,6 +40,28 @@ def driver_argv(ncpu: int, ngpu: int, N: int, NB: int, p: int, q: int, seed: int
     return [str(x) for x in (ncpu, ngpu, N, NB, NB, NB, NB * NB, N, N, 0, 0, N, N, p, q, seed)]
 
 
+def run_in_process(sched: str, N: int, NB: int, seed: int = 42) -> dict:
+    """One grid point on one GPU WITHOUT a child process: the driver's main() is called here and its stdout
+    captured and parsed exactly like the child's (``--in-process``).  The reference always forks
+    (benchmark.c:239-255); on a metered GPU box 560 interpreter + CUDA start-ups cost more than the sweep."""
+    import contextlib
+    import io
+    from . import v6_test
+    os.environ["STARPU_SCHED"] = sched
+    os.environ["CHOL_LOOKAHEAD"] = "0" if sched == "inorder" else "1"
+    buf = io.StringIO()
+    t0 = time.time()
+    try:
+        with contextlib.redirect_stdout(buf):
+            code = v6_test.main(["v6_test"] + driver_argv(0, 1, N, NB, 1, 1, seed))
+    except Exception as e:                          # a crash of the child = non-zero exit, metrics missing
+        sys.stderr.write(f"in-process run failed: {e!r}\n")
+        code = 1
+    ms = int((time.time() - t0) * 1000)
+    gflops, rel = parse_metrics(buf.getvalue())
+    return {"ms": ms, "exit_code": code, "gflops": gflops, "rel_error": rel}
+
+
 def run_one(sched: str, ngpu: int, N: int, NB: int, seed: int = 42, timeout: float | None = None) -> dict:
     from .grid import ProcessGrid
     g = ProcessGrid.for_world(ngpu)
@@ -76,6 +98,8 @@ def main(argv: list[str] | None = None) -> int:
     ap.add_argument("--sched", nargs="*", default=list(SCHEDS))
     ap.add_argument("--repeats", type=int, default=REPEATS)
     ap.add_argument("--csv", default="results/bench.csv")
+    ap.add_argument("--in-process", action="store_true",
+                    help="1 GPU only: call the driver in this process instead of forking one child per run")
     a = ap.parse_args(argv)
     os.makedirs(os.path.dirname(a.csv) or ".", exist_ok=True)
     total = len(a.N) * len(a.NB) * len(a.ngpu) * len(a.sched) * a.repeats
@@ -93,7 +117,7 @@ def main(argv: list[str] | None = None) -> int:
                             step += 1
                             print(f"------------------ sched={sched} N={N} NB={NB} mapping={mapping} étape {step} sur "
                                   f"{total} -----------------------------", flush=True)
-                            res = run_one(sched, ngpu, N, NB)
+                            res = run_in_process(sched, N, NB) if (a.in_process and ngpu == 1) else run_one(sched, ngpu, N, NB)
                             ts = time.strftime("%Y-%m-%d %H:%M:%S")
                             csv.write(f"{ts},{sched},{mapping},0,{ngpu},{N},{NB},{r},{res['ms']},{res['exit_code']},"
                                       f"{res['gflops']:.6f},{res['rel_error']:.6e}\n")

@@ -36,6 +36,7 @@ class TiledCholesky:
     """Plan + executor for the in-place factorization of a TileMatrix (lower, A = L L^T)."""
     trace = None
     tr = None
+    thin_tasks = 0
 
     def __init__(self, A: TileMatrix, group=None, lookahead: bool = True):
         self.A = A
@@ -82,6 +83,10 @@ class TiledCholesky:
             # dist.new_group is collective over ALL ranks: create every column group here, in the
             # same order everywhere, never lazily inside the factorization
             self._make_column_groups()
+        # bulk updates of at most this many tasks run at 1 CTA/SM (see _run); 0 = never.  Measured on 8 B200
+        # (N=65536): 0 -> 393 ms, 40 -> 386, 80 -> 388, 160 -> 414; on one GPU it makes no difference, so it is
+        # on only when several ranks share the panel chain.  CHOL_THIN_TASKS overrides.
+        self.thin_tasks = int(os.environ.get("CHOL_THIN_TASKS", "48" if self.world > 1 else "0"))
         self.update_events = None   # set to [] to time every trailing-update launch (bench.py roofline)
         self.trace = None           # set to [] to record a CUDA-event timeline of the next pass (tools/)
         self._build_plan()
@@ -122,15 +127,16 @@ class TiledCholesky:
     def _k_trsm_panel(self, l_ptr: int, work_ptr: int, tiles_ptr: int, ntiles: int, st: int) -> None:
         _lib.call("chol_trsm_tiles", self.b, l_ptr, self.b, work_ptr, tiles_ptr, ntiles, self.b, None, st)
 
-    def _k_update(self, tasks_ptr: int, ntasks: int, st: int) -> None:
+    def _k_update(self, tasks_ptr: int, ntasks: int, st: int, thin: bool = False) -> None:
         b = self.b
+        occ = 1 if thin else 2
         if self.update_events is None:
-            _lib.call("chol_gemm_tasks", tasks_ptr, ntasks, b, b, b, b, b, b, -1.0, 1.0, st)
+            _lib.call("chol_gemm_tasks_ex", tasks_ptr, ntasks, b, b, b, b, b, b, -1.0, 1.0, occ, st)
             return
         # CUDA events on the launching stream around this one launch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(self.s_update)
-        _lib.call("chol_gemm_tasks", tasks_ptr, ntasks, b, b, b, b, b, b, -1.0, 1.0, st)
+        _lib.call("chol_gemm_tasks_ex", tasks_ptr, ntasks, b, b, b, b, b, b, -1.0, 1.0, occ, st)
         e1.record(self.s_update)
         first = (tasks_ptr - self.d_tasks.data_ptr()) // 32
         nsyrk = int(self.tasks_host[first:first + ntasks, 3].sum()) if 0 <= first < len(self.tasks_host) else 0
@@ -428,7 +434,9 @@ class TiledCholesky:
                         self.s_update.wait_event(step0_gates[1 + g])
                         self._k_update(base + (na + t0) * 32, t1 - t0, st)
                 elif ntot > na:
-                    self._k_update(base + na * 32, ntot - na, st)
+                    # the bulk of the update overlaps panel step k+1: once it is small enough for that panel
+                    # chain to bound the step, it runs at one CTA per SM and leaves the chain's kernels room
+                    self._k_update(base + na * 32, ntot - na, st, thin=0 < ntot - na <= self.thin_tasks)
                 ev_upd[k % ns] = self._record()
                 self._mark("upd1", k, self.s_update)
                 self._release_panel(k, ev_upd[k % ns])
@@ -617,6 +625,17 @@ def potrf_tile_desc(uplo: str, A: TileMatrix, group=None, lookahead: bool = True
     the reference calls."""
     if uplo not in ("L", "l"):
         raise ValueError("only uplo='L' (ChamLower) is supported")
-    ch = TiledCholesky(A, group=group, lookahead=lookahead)
+    # one plan (and, on several ranks, one set of communicators / peer buffers) per descriptor storage:
+    # repeated calls on the same matrix must not create new process groups every time
+    key = (A.desc, A.rank, A.buf.data_ptr(), lookahead, id(group))
+    ch = _plans.get(key)
+    if ch is None:
+        if len(_plans) >= 8:
+            _, old = _plans.popitem()
+            old.close()
+        ch = _plans[key] = TiledCholesky(A, group=group, lookahead=lookahead)
     ch.factor()
     return ch.info()
+
+
+_plans: dict = {}

@@ -45,7 +45,7 @@ int ensure_init() {
                              int(GemmWide::SMEM_BYTES));
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmWide>)");
     e = cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(GemmPair::SMEM_BYTES));
+                             int(120 * 1024));
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmPair>)");
     e = cudaFuncSetAttribute(gemm_nt_dmma_kernel<GemmPair>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
@@ -85,6 +85,8 @@ int ensure_init() {
 
 namespace {
 
+constexpr size_t GEMM_THIN_SMEM = 120 * 1024;
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 GemmParams make_params(int ntasks, int m, int n, int k, int lda, int ldb, int ldc, double alpha, double beta) {
@@ -103,7 +105,7 @@ GemmParams make_params(int ntasks, int m, int n, int k, int lda, int ldb, int ld
 // `inplace_tri`: the tasks have C == A, beta == 0 and B lower triangular (the multiply step of
 // the blocked TRSM); the fast path handles the aliasing by giving all n (<= 128) columns of a row
 // block to ONE CTA, the generic path has an alias-safe kernel.
-int launch_gemm(GemmParams p, cudaStream_t st, bool inplace_tri = false) {
+int launch_gemm(GemmParams p, cudaStream_t st, bool inplace_tri = false, bool thin = false) {
     const int ntasks = p.ntasks, m = p.m, n = p.n, k = p.k;
     if (ntasks <= 0 || m <= 0 || n <= 0) return 0;
     const bool single = !p.tasks && !p.tile_ptrs;
@@ -122,7 +124,10 @@ int launch_gemm(GemmParams p, cudaStream_t st, bool inplace_tri = false) {
         if (wide)
             gemm_nt_dmma_kernel<GemmWide><<<dim3((unsigned)grid), GemmWide::THREADS, GemmWide::SMEM_BYTES, st>>>(p);
         else
-            gemm_nt_dmma_kernel<GemmPair><<<dim3((unsigned)grid), GemmPair::THREADS, GemmPair::SMEM_BYTES, st>>>(p);
+            // `thin`: ask for more dynamic shared memory than the kernel uses so that only ONE CTA fits per SM and
+            // the other half of every SM stays free for the panel kernels of the next step
+            gemm_nt_dmma_kernel<GemmPair><<<dim3((unsigned)grid), GemmPair::THREADS,
+                                            thin ? GEMM_THIN_SMEM : GemmPair::SMEM_BYTES, st>>>(p);
         CHECK_LAUNCH("gemm_nt_dmma_kernel");
         return 0;
     }
@@ -157,12 +162,14 @@ inline bool fast32(int b, int lda, int ldl, const void* a, const void* l) {
 // X = A L_jj^{-T} on the 128-column block at `off` of one matrix (`single`) or of every tile of a
 // pointer list: m rows, nbv (multiple of 32) columns.
 int launch_leaf(double* const* d_tiles, double* single, int ntiles, long long off, int m, int nbv, int lda,
-                const double* Ljj, int ldl, const double* Dinv, cudaStream_t st) {
+                const double* Ljj, int ldl, const double* Dinv, cudaStream_t st, const long long* peer_dst = nullptr,
+                int npeer = 0) {
     if (ntiles <= 0 || m <= 0 || nbv <= 0) return 0;
     LeafParams p;
     p.tile_ptrs = d_tiles; p.single = single; p.off = off;
     p.m = m; p.nbk = nbv / SB; p.lda = lda;
     p.L = Ljj; p.ldl = ldl; p.Dinv = Dinv;
+    p.peer_dst = peer_dst; p.npeer = peer_dst ? npeer : 0;
     p.ctas_per_task = (m + LF_ROWS - 1) / LF_ROWS;
     const long long grid = (long long)ntiles * p.ctas_per_task;
     if (grid > 0x7fffffffLL) return fail_arg(6, "chol_trsm_tiles", "too many CTAs");
@@ -186,6 +193,8 @@ struct TrsmCtx {
     int ntiles, lda;
     cudaStream_t st;
     bool v2;        // leaves by block substitution with the 32x32 inverses (trsm_leaf32_kernel)
+    const long long* peer_dst;   // fused push of the finished column blocks into peers' slots (v2 only)
+    int npeer;
 };
 
 int trsm_issue(const TrsmCtx& c, long long c_off, long long a_off, const double* B, int n, int k, int ldb,
@@ -205,7 +214,8 @@ int trsm_rec(const TrsmCtx& c, int lo, int hi) {
         const int nbv = (c.b - o < NBD) ? c.b - o : NBD;
         if (c.v2)
             return launch_leaf(c.d_tiles, c.single, c.ntiles, (long long)o * c.lda, c.b, nbv, c.lda,
-                               c.L + size_t(o) * c.ldl + o, c.ldl, c.Winv + size_t(lo) * NBD * NBD, c.st);
+                               c.L + size_t(o) * c.ldl + o, c.ldl, c.Winv + size_t(lo) * NBD * NBD, c.st, c.peer_dst,
+                               c.npeer);
         return trsm_issue(c, (long long)o * c.lda, (long long)o * c.lda, c.Winv + size_t(lo) * NBD * NBD, nbv, nbv, NBD,
                           1.0, 0.0, true);
     }
@@ -220,10 +230,11 @@ int trsm_rec(const TrsmCtx& c, int lo, int hi) {
 }
 
 int trsm_sweep(int b, const double* L, int ldl, const double* Winv, double* const* d_tiles, double* single,
-               int ntiles, int lda, cudaStream_t st) {
+               int ntiles, int lda, cudaStream_t st, const long long* peer_dst = nullptr, int npeer = 0) {
     // (the tiles of a pointer list are 16-byte aligned by contract, see chol_b200.h)
     const bool v2 = fast32(b, lda, ldl, single ? (const void*)single : (const void*)L, L) && aligned16(Winv);
-    TrsmCtx c{b, L, ldl, Winv, d_tiles, single, ntiles, lda, st, v2};
+    if (peer_dst && !v2) return fail_arg(1, "chol_trsm_tiles_push", "the fused push needs tiles that are multiples of 32");
+    TrsmCtx c{b, L, ldl, Winv, d_tiles, single, ntiles, lda, st, v2, peer_dst, npeer};
     return trsm_rec(c, 0, (b + NBD - 1) / NBD);
 }
 
@@ -255,6 +266,21 @@ int chol_gemm_tasks(const chol_task_t* d_tasks, int ntasks, int m, int n, int k,
     GemmParams p = make_params(ntasks, m, n, k, lda, ldb, ldc, alpha, beta);
     p.tasks = d_tasks;
     return launch_gemm(p, (cudaStream_t)stream);
+}
+
+int chol_gemm_tasks_ex(const chol_task_t* d_tasks, int ntasks, int m, int n, int k, int lda, int ldb, int ldc,
+                       double alpha, double beta, int ctas_per_sm, void* stream) {
+    if (ctas_per_sm != 1 && ctas_per_sm != 2) return fail_arg(11, "chol_gemm_tasks_ex", "ctas_per_sm (1 or 2)");
+    if (ntasks < 0) return fail_arg(2, "chol_gemm_tasks_ex", "ntasks");
+    if (ntasks > 0 && !d_tasks) return fail_arg(1, "chol_gemm_tasks_ex", "d_tasks");
+    if (m < 0 || n < 0 || k < 0) return fail_arg(3, "chol_gemm_tasks_ex", "m / n / k");
+    if (lda < (m > 1 ? m : 1)) return fail_arg(6, "chol_gemm_tasks_ex", "lda");
+    if (ldb < (n > 1 ? n : 1)) return fail_arg(7, "chol_gemm_tasks_ex", "ldb");
+    if (ldc < (m > 1 ? m : 1)) return fail_arg(8, "chol_gemm_tasks_ex", "ldc");
+    if (int rc = ensure_init()) return rc;
+    GemmParams p = make_params(ntasks, m, n, k, lda, ldb, ldc, alpha, beta);
+    p.tasks = d_tasks;
+    return launch_gemm(p, (cudaStream_t)stream, false, ctas_per_sm == 1);
 }
 
 size_t chol_potrf_tile_workspace(int b) {
@@ -336,6 +362,23 @@ int chol_trsm_tiles(int b, const double* L, int ldl, const double* potrf_work, d
     if (int rc = ensure_init()) return rc;
     (void)d_task_scratch;
     return trsm_sweep(b, L, ldl, potrf_work, d_tiles, nullptr, ntiles, lda, (cudaStream_t)stream);
+}
+
+int chol_trsm_tiles_push(int b, const double* L, int ldl, const double* potrf_work, double* const* d_tiles, int ntiles,
+                         int lda, const long long* d_peer_dst, int npeer, void* stream) {
+    if (b < 0) return fail_arg(1, "chol_trsm_tiles_push", "b");
+    if (ntiles < 0) return fail_arg(6, "chol_trsm_tiles_push", "ntiles");
+    if (npeer < 0 || npeer > LF_MAX_PEERS) return fail_arg(9, "chol_trsm_tiles_push", "npeer (at most 7)");
+    if (b == 0 || ntiles == 0) return 0;
+    if (!L) return fail_arg(2, "chol_trsm_tiles_push", "L");
+    if (ldl < b) return fail_arg(3, "chol_trsm_tiles_push", "ldl");
+    if (!potrf_work) return fail_arg(4, "chol_trsm_tiles_push", "potrf_work");
+    if (!d_tiles) return fail_arg(5, "chol_trsm_tiles_push", "d_tiles");
+    if (lda < b) return fail_arg(7, "chol_trsm_tiles_push", "lda");
+    if (npeer > 0 && !d_peer_dst) return fail_arg(8, "chol_trsm_tiles_push", "d_peer_dst");
+    if (int rc = ensure_init()) return rc;
+    return trsm_sweep(b, L, ldl, potrf_work, d_tiles, nullptr, ntiles, lda, (cudaStream_t)stream,
+                      npeer > 0 ? d_peer_dst : nullptr, npeer);
 }
 
 int chol_syrk_tile(int b, const double* A, int lda, double* C, int ldc, void* stream) {

@@ -139,9 +139,40 @@ __device__ __forceinline__ chol_task_t load_task(const GemmParams& p, int task_i
     return task;
 }
 
+// Slow path of one CTA tile for tasks whose pointers are not 16-byte aligned.  Inlined on purpose: the CTA
+// returns right after it, so its few registers never overlap the accumulators' live range, while an
+// out-of-line call gives the kernel a stack frame and ABI spills (ptxas: 96 B stack, 80 B spill stores).
+__device__ __forceinline__ void gemm_block_scalar(const GemmParams& p, const chol_task_t& task, bool lower, int row0,
+                                               int col0, int mv, int nv) {
+    for (int idx = threadIdx.x; idx < mv * nv; idx += blockDim.x) {
+        const int i = row0 + idx % mv, j = col0 + idx / mv;
+        if (lower && i < j) continue;
+        double s = 0.0;
+        for (int l = 0; l < p.k; ++l) s = fma(task.A[size_t(l) * p.lda + i], task.B[size_t(l) * p.ldb + j], s);
+        double* c = task.C + size_t(j) * p.ldc + i;
+        double v = p.alpha * s;
+        if (p.beta != 0.0) v += p.beta * *c;
+        *c = v;
+    }
+}
+
 // ---- the kernel --------------------------------------------------------------------
+// One CTA per 128 x BN tile, scheduled by the hardware.  A persistent variant (grid = resident CTAs, each
+// walking tiles grid-stride with the producer warp running ahead into the next tile) was measured on B200 and
+// dropped: 31.4 / 32.5 TFLOP/s against 33.5 / 34.0 for this form at 120 / 820 tasks — the two CTAs of an SM
+// fall into step and reach their epilogues together, and the per-tile task fetch sits on the consumers' path,
+// while fresh CTAs handed out by the hardware stay staggered.
+#ifndef CHOL_GEMM_MAXNREG
+#define CHOL_GEMM_MAXNREG 0
+#endif
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
+__global__ void
+#if CHOL_GEMM_MAXNREG > 0
+__maxnreg__(CHOL_GEMM_MAXNREG)
+#else
+__launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS)
+#endif
+gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
     constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES, STAGE_DOUBLES = Cfg::STAGE_DOUBLES;
     constexpr int SLAB_DOUBLES = Cfg::SLAB_A, PITCH_B = Cfg::PITCH_B;
     constexpr int GEMM_CONSUMER_WARPS = Cfg::CONSUMER_WARPS;
@@ -167,6 +198,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+
+    // The host checks the 16-byte alignment the bulk copies and the 16-byte C accesses need only for a
+    // single task; the pointers of a device task list / tile list are checked here, per task.  A task
+    // that is merely 8-byte aligned is computed by this CTA with plain FMAs (slow, correct) instead of
+    // raising a misaligned-address fault that would kill the context.  C == A (the in-place multiply)
+    // cannot take this path and is rejected on the host when misaligned.
+    if (((reinterpret_cast<uintptr_t>(task.C) | reinterpret_cast<uintptr_t>(task.A) |
+          reinterpret_cast<uintptr_t>(task.B)) & 15u) != 0) {
+        gemm_block_scalar(p, task, lower, row0, col0, mv, nv);
+        return;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -269,15 +311,18 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
     const double alpha = p.alpha, beta = p.beta;
     const bool diag_block = lower && (col0 + BN > row0);   // block touches the diagonal
     double* gC = task.C + size_t(col0) * p.ldc + row0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    // One group = the 16 rows q, the 16-column halves r_lo .. r_hi-1 and elements e_lo .. e_hi-1 of this warp's
+    // sub-tile.  While all 64 accumulators are still live the groups are small (2, 2, then 4 loads in flight),
+    // from q == 1 on a group is 8 loads: the full batch from the start costs 120 bytes of spills under the
+    // 168-register cap ptxas applies for two 5-warp CTAs per SM (ptxas -v; now 0 spills).
+    auto group = [&](const int q, const int r_lo, const int r_hi, const int e_lo = 0, const int e_hi = 2) {
         const int r_loc = wm * 64 + q * 16 + 2 * g;  // first of the two rows this lane owns
-        if (r_loc >= mv) continue;                   // mv is even: the pair is in or out together
+        if (r_loc >= mv) return;                     // mv is even: the pair is in or out together
         double2 old[2][2][2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = r_lo; r < r_hi; ++r)
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
+            for (int e = e_lo; e < e_hi; ++e)
 #pragma unroll
                 for (int np = 0; np < 2; ++np) {
                     const int c_loc = wn * 32 + r * 16 + 4 * t + 2 * e + np;
@@ -290,9 +335,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
                         old[r][e][np].y = ptr[1];     // the pair straddles the diagonal: lower element only
                 }
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = r_lo; r < r_hi; ++r)
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
+            for (int e = e_lo; e < e_hi; ++e)
 #pragma unroll
                 for (int np = 0; np < 2; ++np) {
                     const int c_loc = wn * 32 + r * 16 + 4 * t + 2 * e + np;
@@ -311,7 +356,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) gemm_nt_dmma_kern
                     }
                     *reinterpret_cast<double2*>(ptr) = make_double2(v0, v1);
                 }
-    }
+    };
+    group(0, 0, 1, 0, 1);
+    group(0, 0, 1, 1, 2);
+    group(0, 1, 2);
+    group(1, 0, 2);
+    group(2, 0, 2);
+    group(3, 0, 2);
 }
 
 // ---- generic fallback for shapes the fast path cannot take (odd sizes, unaligned) ------

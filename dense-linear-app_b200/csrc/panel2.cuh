@@ -242,7 +242,14 @@ struct LeafParams {
     int ldl;
     const double* Dinv;
     int ctas_per_task;
+    // fused panel push (multi-GPU): task t also stores its result into the receive slots of up to
+    // LF_MAX_PEERS ranks — peer_dst[t * npeer + q] is the address of this tile in peer q's mapped
+    // slot buffer, 0 = that peer does not read this tile.  The transfer over NVLink then overlaps the
+    // solve column block by column block instead of following it as a copy.
+    const long long* peer_dst;
+    int npeer;
 };
+constexpr int LF_MAX_PEERS = 7;
 
 // one 16 x 32 x 32 product on the DMMA pipe: acc (+)= stg(16 x 32, A operand) * B^T, B (32 x 32) column-major
 // at `B` with leading dimension ldb in global memory (read-only during the kernel); NEG subtracts.
@@ -272,7 +279,7 @@ __device__ __forceinline__ void leaf_product(double (&acc)[2][2][2][2], const do
     }
 }
 
-__global__ void __launch_bounds__(LF_THREADS, 3) trsm_leaf32_kernel(const __grid_constant__ LeafParams p) {
+__global__ void __launch_bounds__(LF_THREADS, 2) trsm_leaf32_kernel(const __grid_constant__ LeafParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* stage_all = reinterpret_cast<double*>(smem_raw);                    // 4 warps x (32 cols x LF_SP)
     const int tid = threadIdx.x, lane = tid & 31;
@@ -282,11 +289,32 @@ __global__ void __launch_bounds__(LF_THREADS, 3) trsm_leaf32_kernel(const __grid
     const int rb = blockIdx.x - task * p.ctas_per_task;
     double* Abase = (p.tile_ptrs ? p.tile_ptrs[task] : p.single) + p.off;
     const int nbk = p.nbk;
+    if ((reinterpret_cast<uintptr_t>(Abase) & 15u) != 0) {
+        // a tile of the pointer list that is only 8-byte aligned (the host cannot see device pointer lists):
+        // plain forward substitution, one thread per row — slow, correct, and no misaligned 16-byte access
+        const int ncol = nbk * SB;
+        for (int row = rb * LF_ROWS + tid; row < min(p.m, (rb + 1) * LF_ROWS); row += LF_THREADS) {
+            double* a = Abase + row;
+            for (int c = 0; c < ncol; ++c) {
+                double sacc = a[size_t(c) * p.lda];
+                for (int k = 0; k < c; ++k) sacc = fma(-a[size_t(k) * p.lda], p.L[size_t(k) * p.ldl + c], sacc);
+                a[size_t(c) * p.lda] = sacc / p.L[size_t(c) * p.ldl + c];
+            }
+        }
+        return;
+    }
     // warp w owns rows row0 .. row0 + 15 of this CTA's strip, as DMMA accumulators, from load to store
     const int row0 = rb * LF_ROWS + warp * 16;
     const bool live = row0 + 2 * g < p.m;                  // m is even: the row pair is in or out together
     double* gA = Abase + row0 + 2 * g;
     double* stg = stage_all + warp * SB * LF_SP;
+    double* gP[LF_MAX_PEERS];                               // the same rows of this tile in the peers' slots
+#pragma unroll
+    for (int q = 0; q < LF_MAX_PEERS; ++q) {
+        long long d = 0;
+        if (q < p.npeer) d = __ldg(p.peer_dst + size_t(task) * p.npeer + q);
+        gP[q] = d ? reinterpret_cast<double*>(d) + p.off + row0 + 2 * g : nullptr;
+    }
     double acc[4][2][2][2][2];                              // [block][r][mp][np][e]
 #pragma unroll
     for (int I = 0; I < 4; ++I)
@@ -335,7 +363,12 @@ __global__ void __launch_bounds__(LF_THREADS, 3) trsm_leaf32_kernel(const __grid
                         const double2 v = make_double2(x[r][0][np][e], x[r][1][np][e]);
                         const int c = r * 16 + 4 * t + 2 * e + np;
                         *reinterpret_cast<double2*>(stg + c * LF_SP + 2 * g) = v;
-                        if (live) *reinterpret_cast<double2*>(gA + size_t(J * SB + c) * p.lda) = v;
+                        if (live) {
+                            *reinterpret_cast<double2*>(gA + size_t(J * SB + c) * p.lda) = v;
+#pragma unroll
+                            for (int q = 0; q < LF_MAX_PEERS; ++q)
+                                if (gP[q]) *reinterpret_cast<double2*>(gP[q] + size_t(J * SB + c) * p.lda) = v;
+                        }
                     }
             __syncwarp();
             // A_I -= X_J L_IJ^T for the blocks to the right

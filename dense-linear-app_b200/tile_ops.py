@@ -89,3 +89,55 @@ def potrf_batched(A: torch.Tensor) -> torch.Tensor:
     info = torch.zeros(max(batch, 1), dtype=torch.int32, device=A.device)
     _lib.call("chol_potrf_batched", n, batch, A.data_ptr(), n, n * n, info.data_ptr(), _stream(A))
     return info[:batch]
+
+
+def potrf_batched_from_host(host_in: torch.Tensor, host_out: torch.Tensor, host_info: torch.Tensor,
+                            device: torch.device | None = None, chunks: int = 16) -> None:
+    """End-to-end form of potrf_batched for matrices that live in (pinned) HOST memory — the many-task
+    situation of the ArmoniK worker, where every tile arrives as a host blob (worker_distrib.cpp:186,261).
+    The batch is cut into `chunks` pieces that flow through three streams: upload of piece i+1, factorization
+    of piece i and download of piece i-1 overlap, so the step costs about max(PCIe in, PCIe out, kernel)
+    instead of their sum.  Asynchronous on the current stream; synchronise before reading host_out."""
+    if not (host_in.is_pinned() and host_out.is_pinned() and host_info.is_pinned()):
+        raise ValueError("potrf_batched_from_host: host tensors must be pinned")
+    if host_in.dtype != torch.float64 or host_in.dim() != 3 or host_in.shape[1] != host_in.shape[2]:
+        raise ValueError("potrf_batched_from_host: host_in must be float64 [batch, n, n]")
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    batch, n = host_in.shape[0], host_in.shape[1]
+    per = -(-batch // max(1, chunks))
+    key = (dev.index, per, n)
+    st = _pipelines.get(key)
+    if st is None:
+        st = _pipelines[key] = {"buf": [torch.empty((per, n, n), dtype=torch.float64, device=dev) for _ in range(3)],
+                                "info": [torch.zeros(per, dtype=torch.int32, device=dev) for _ in range(3)],
+                                "up": torch.cuda.Stream(dev), "run": torch.cuda.Stream(dev), "down": torch.cuda.Stream(dev),
+                                "free": [None, None, None]}
+    cur = torch.cuda.current_stream(dev)
+    for s_ in (st["up"], st["run"], st["down"]):
+        s_.wait_stream(cur)
+    for i, lo in enumerate(range(0, batch, per)):
+        hi = min(batch, lo + per)
+        slot = i % 3
+        buf, inf = st["buf"][slot][:hi - lo], st["info"][slot][:hi - lo]
+        with torch.cuda.stream(st["up"]):
+            if st["free"][slot] is not None:
+                st["up"].wait_event(st["free"][slot])          # the download that last used this slot
+            buf.copy_(host_in[lo:hi], non_blocking=True)
+            ev_up = torch.cuda.Event()
+            ev_up.record(st["up"])
+        with torch.cuda.stream(st["run"]):
+            st["run"].wait_event(ev_up)
+            _lib.call("chol_potrf_batched", n, hi - lo, buf.data_ptr(), n, n * n, inf.data_ptr(), st["run"].cuda_stream)
+            ev_run = torch.cuda.Event()
+            ev_run.record(st["run"])
+        with torch.cuda.stream(st["down"]):
+            st["down"].wait_event(ev_run)
+            host_out[lo:hi].copy_(buf, non_blocking=True)
+            host_info[lo:hi].copy_(inf, non_blocking=True)
+            st["free"][slot] = torch.cuda.Event()
+            st["free"][slot].record(st["down"])
+    for s_ in (st["up"], st["run"], st["down"]):
+        cur.wait_stream(s_)
+
+
+_pipelines: dict = {}

@@ -131,11 +131,12 @@ def main(argv: list[str] | None = None) -> int:
     except ValueError as e:
         sys.stderr.write(f"Error: {e}\n")
         return 1
-    ch = TiledCholesky(A)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
+    # task submission (the plan) is part of CHAMELEON_dpotrf_Tile's bracket (v3_script_cholesky_x_arg_gpt.c:224-228)
     t0 = time.monotonic()
+    ch = TiledCholesky(A)
     ch.factor()
     info = ch.info()
     time_sec = time.monotonic() - t0

@@ -56,11 +56,21 @@ def main(argv: list[str] | None = None) -> int:
     desc = TileDesc(mb, nb, max(bsiz, mb * nb), lm, ln, ioff, joff, m, n, p, q)
     A = TileMatrix(desc, rank).generate(float(N), seed)                      # dplgsy(bump = N)
     Aorig = A.clone()                                                        # dlacpy(UpperLower)
-    ch = TiledCholesky(A, lookahead=os.environ.get("CHOL_LOOKAHEAD", "1") != "0")
+    lookahead = os.environ.get("CHOL_LOOKAHEAD", "1") != "0"
+    if world == 1:
+        # what CHAMELEON_Init does for its codelets (cuBLAS handles, v6_test.c:41): load the kernels of this
+        # tile size once, outside the timed region, on a 2 x 2-tile dummy
+        W = TileMatrix(TileDesc.square(2 * mb, mb), 0).generate(float(2 * mb), 1)
+        TiledCholesky(W, lookahead=lookahead).factor()
+        del W
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
+    # the reference times all of CHAMELEON_dpotrf_Tile, task submission included (v6_test.c:54-57):
+    # building the plan (the DAG as device task lists) is inside the bracket
     t0 = time.monotonic()
+    ch = TiledCholesky(A, lookahead=lookahead)
+    t_plan = time.monotonic() - t0
     ch.factor()
     info = ch.info()                                                          # synchronises
     t1 = time.monotonic()
@@ -68,6 +78,7 @@ def main(argv: list[str] | None = None) -> int:
     gflops = (1.0 / 3.0) * float(N) ** 3 / (time_sec * 1e9)
     out(f"N = {N}, NB = {NB}")
     out(f"Time: {time_sec:.3f} s")
+    out(f"[plan] {t_plan * 1e3:.1f} ms of it building and uploading the task lists")
     out(f"Performance: {gflops:.2f} Gflop/s")
     if info != 0:
         sys.stderr.write(f"Erreur dans CHAMELEON_dpotrf_Tile: {info}\n")

@@ -67,11 +67,21 @@ typedef struct chol_task {
 /* All tasks share m, n, k and the leading dimensions.  `d_tasks` is a DEVICE array.
  * Replaces the per-tile SYRK/GEMM submissions of one wave of the client loop
  * (C1:307-329, C2:541-561) by ONE persistent launch: the "fused SYRK+GEMM trailing
- * update per panel".  Fast path (DMMA + TMA bulk staging) needs m,n even, k%4==0,
- * even leading dimensions and 16-byte aligned tile pointers; other shapes take the
- * generic CUDA kernel. */
+ * update per panel".  Fast path (DMMA + TMA bulk staging) needs m,n even, k%4==0 and
+ * even leading dimensions; other shapes take the generic CUDA kernel.  Tile pointers should be
+ * 16-byte aligned: a task of the list whose pointers are only 8-byte aligned is still computed
+ * correctly, by a slow scalar path inside the kernel (the pointers live in device memory, so
+ * the host cannot pre-check them). */
 int chol_gemm_tasks(const chol_task_t* d_tasks, int ntasks, int m, int n, int k,
                     int lda, int ldb, int ldc, double alpha, double beta, void* stream);
+
+/* Same, with the residency of the update grid chosen by the caller: ctas_per_sm = 2 is chol_gemm_tasks;
+ * ctas_per_sm = 1 leaves half of every SM free, so that the (short, latency-critical) panel kernels
+ * of the next step find a free slot at once instead of waiting for update CTAs to retire.  The
+ * whole-matrix driver uses it for the last steps, where the panel chain bounds the step time. */
+int chol_gemm_tasks_ex(const chol_task_t* d_tasks, int ntasks, int m, int n, int k,
+                       int lda, int ldb, int ldc, double alpha, double beta, int ctas_per_sm,
+                       void* stream);
 
 /* ---- the four tile ops of the worker (W2:179-546) -------------------------------- */
 
@@ -99,6 +109,16 @@ int chol_trsm_tile(int b, const double* L, int ldl, double* A, int lda, double* 
 int chol_trsm_tiles(int b, const double* L, int ldl, const double* potrf_work,
                     double* const* d_tiles, int ntiles, int lda, void* d_task_scratch,
                     void* stream);
+
+/* Panel form fused with the panel transport (multi-GPU, tile sizes that are multiples of 32): as
+ * chol_trsm_tiles, and every finished 128-column block of tile t is ALSO stored, by the kernel that
+ * computes it, into up to 7 peers' receive slots over NVLink — d_peer_dst[t*npeer + q] is the address
+ * of tile t in peer q's mapped slot buffer (chol_peer_open), 0 if that peer does not read the tile.
+ * The transfer overlaps the solve instead of following it as a copy; raise the peers' flags with
+ * chol_flag_post on the same stream afterwards. */
+int chol_trsm_tiles_push(int b, const double* L, int ldl, const double* potrf_work,
+                         double* const* d_tiles, int ntiles, int lda,
+                         const long long* d_peer_dst, int npeer, void* stream);
 
 /* SYRK: C <- C - A*A^T, lower triangle only.
  * Replaces CHAMELEON_dsyrk_Tile(ChamLower,ChamNoTrans,-1.0,dA,1.0,dC) (W2:416). */

@@ -28,7 +28,7 @@ class OracleBackedCholesky(TiledCholesky):
         for t in range(ntiles):
             O.lib().oracle_trsm_tile(self.b, self.b, l_ptr, self.b, ptrs[t], self.b)
 
-    def _k_update(self, tasks_ptr, ntasks, st):
+    def _k_update(self, tasks_ptr, ntasks, st, thin=False):
         rec = np.ctypeslib.as_array((C.c_int64 * (4 * ntasks)).from_address(tasks_ptr)).reshape(ntasks, 4)
         b = self.b
         for c, a, bb, flag in rec.tolist():

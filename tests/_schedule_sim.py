@@ -258,7 +258,7 @@ class RankSim(TiledCholesky):
         tl = {self.region(p) for p in (C.c_int64 * ntiles).from_address(tiles_ptr)}
         self.op("trsm", tl | {self.region(l_ptr), self.region(work_ptr)}, tl)
 
-    def _k_update(self, tasks_ptr, ntasks, st):
+    def _k_update(self, tasks_ptr, ntasks, st, thin=False):
         rec = np.ctypeslib.as_array((C.c_int64 * (4 * ntasks)).from_address(tasks_ptr)).reshape(ntasks, 4)
         w = {self.region(c) for c in rec[:, 0].tolist()}
         r = {self.region(p) for p in rec[:, 1].tolist()} | {self.region(p) for p in rec[:, 2].tolist()}

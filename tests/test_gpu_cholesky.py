@@ -264,6 +264,27 @@ def test_potrf_batched_strided_through_the_c_abi(cuda_lib, oracle, n, lda, pad):
         assert np.all(out[i * stride + lda * n:(i + 1) * stride] == -7.5)
 
 
+def test_potrf_batched_from_host_matches_device_path(cuda_lib, oracle):
+    """Host-resident batch through the three-stream pipeline == the device path, info included."""
+    from dense_linear_app_b200 import tile_ops
+    n, batch = 96, 53
+    mats = [oracle.plgsy(float(n), n, 7 + i) for i in range(batch)]
+    mats[11] = mats[11].copy()
+    mats[11][40, 40] = -3.0
+    host = torch.from_numpy(np.stack([np.ascontiguousarray(m.T) for m in mats])).pin_memory()
+    out = torch.empty_like(host).pin_memory()
+    hinfo = torch.empty(batch, dtype=torch.int32).pin_memory()
+    for chunks in (1, 4, 16, 100):
+        out.zero_()
+        tile_ops.potrf_batched_from_host(host, out, hinfo, chunks=chunks)
+        torch.cuda.current_stream().synchronize()
+        d = host.cuda()
+        info = tile_ops.potrf_batched(d)
+        # bit patterns, not values: the matrix with the bad pivot holds NaNs past the failure
+        assert torch.equal(out.cuda().view(torch.int64), d.view(torch.int64)) and torch.equal(hinfo.cuda(), info)
+        assert int(hinfo[11]) == 41 and int((hinfo != 0).sum()) == 1
+
+
 def test_potrf_batched_config4_full_size_properties(cuda_lib):
     """BASELINE configs[4] at its full size (10 000 x 256): info == 0 everywhere and the backward
     error ||A - L L^T||_F / ||A||_F of EVERY matrix <= 1e-13 (checked with torch.bmm, the checker)."""

@@ -156,6 +156,49 @@ def test_grouped_update_matches_tile_ops(cuda_lib):
     assert torch.equal(C, C2)
 
 
+def test_task_lists_with_8_byte_aligned_tiles(cuda_lib, oracle):
+    """Device task lists and tile-pointer lists cannot be alignment-checked on the host: tiles that are
+    only 8-byte aligned must still be computed correctly (slow in-kernel path), not fault the context."""
+    from dense_linear_app_b200 import _lib
+    lib = _lib.load()
+    b = 64
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(7)
+    pool = torch.zeros(8 * b * b + 16, dtype=torch.float64, device="cuda")
+
+    def place(k, host):                      # tile k at an ODD double offset -> 8-byte aligned only
+        off = k * b * b + 1
+        pool[off:off + b * b] = torch.from_numpy(np.ascontiguousarray(host.T).reshape(-1)).cuda()
+        return pool.data_ptr() + off * 8, off
+
+    Ah, Bh, Ch = (np.asfortranarray(rng.uniform(-0.5, 0.5, (b, b))) for _ in range(3))
+    pa, _ = place(0, Ah)
+    pb, _ = place(1, Bh)
+    pc, oc = place(2, Ch)
+    assert pc % 16 == 8
+    tasks = torch.tensor([[pc, pa, pb, 0]], dtype=torch.int64, device="cuda")
+    _lib.call("chol_gemm_tasks", tasks.data_ptr(), 1, b, b, b, b, b, b, -1.0, 1.0, st)
+    got = pool[oc:oc + b * b].reshape(b, b).cpu().numpy().T
+    ref = Ch.copy(order="F")
+    oracle.gemm_tile(Ah, Bh, ref)
+    assert np.abs(got - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+    # panel TRSM on a misaligned tile (aligned L and workspace)
+    S = np.asfortranarray(Ah @ Ah.T + b * np.eye(b))
+    dS = dev_cm(S)
+    work = torch.empty(max(lib.chol_potrf_tile_workspace(b) // 8, 1), dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.call("chol_potrf_tile", b, dS.data_ptr(), b, work.data_ptr(), info.data_ptr(), 0, st)
+    pt, ot = place(3, Bh)
+    ptrs = torch.tensor([pt], dtype=torch.int64, device="cuda")
+    _lib.call("chol_trsm_tiles", b, dS.data_ptr(), b, work.data_ptr(), ptrs.data_ptr(), 1, b, None, st)
+    torch.cuda.synchronize()
+    got = pool[ot:ot + b * b].reshape(b, b).cpu().numpy().T
+    L = np.asfortranarray(np.tril(host_cm(dS)))
+    ref = Bh.copy(order="F")
+    oracle.trsm_tile(L, ref)
+    assert np.abs(got - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+
+
 def test_tile_ops_reject_cpu_tensors():
     from dense_linear_app_b200 import _lib, tile_ops
     with pytest.raises(_lib.CholError):

@@ -128,7 +128,7 @@ class Probe(TiledCholesky):
         tl = {self.region(p) for p in ptrs}
         self.op("trsm", st, tl | {self.region(l_ptr), ("W",)}, tl)
 
-    def _k_update(self, tasks_ptr, ntasks, st):
+    def _k_update(self, tasks_ptr, ntasks, st, thin=False):
         rec = np.ctypeslib.as_array((C.c_int64 * (4 * ntasks)).from_address(tasks_ptr)).reshape(ntasks, 4)
         w = {self.region(c) for c in rec[:, 0].tolist()}
         r = {self.region(p) for p in rec[:, 1].tolist()} | {self.region(p) for p in rec[:, 2].tolist()}
