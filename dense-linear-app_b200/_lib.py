@@ -37,6 +37,8 @@ SIGNATURES = {
     "chol_peer_send": (c_int, [c_void_p, c_int, c_void_p]),
     "chol_flag_wait": (c_int, [c_void_p, C.c_uint32, c_void_p]),
     "chol_flag_post": (c_int, [c_void_p, c_int, C.c_uint32, c_void_p]),
+    "chol_partition_create": (c_int, [c_int, c_int, c_void_p]),
+    "chol_partition_destroy": (c_int, [c_void_p]),
     "chol_plgsy_tile": (c_int, [c_double, c_int, c_int, c_void_p, c_int, c_ll, c_ll, c_ll, c_ll, c_ull, c_void_p]),
     "chol_tile_sumsq": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "chol_tile_abs_sums": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -50,6 +52,12 @@ class Xfer(C.Structure):
     _fields_ = [("dst", c_void_p), ("src", c_void_p), ("tile_bytes", c_ll), ("count", c_int), ("dst_stride", c_int),
                 ("src_stride", c_int), ("credit_value", C.c_uint32), ("credit", c_void_p), ("flag", c_void_p),
                 ("flag_value", C.c_uint32), ("reserved", C.c_uint32), ("stream", c_void_p)]
+
+
+class Partition(C.Structure):
+    """chol_partition_t (include/chol_b200.h)."""
+    _fields_ = [("handle", c_void_p), ("panel_stream", c_void_p), ("rest_stream", c_void_p), ("panel_sms", c_int),
+                ("rest_sms", c_int)]
 
 
 class CholError(RuntimeError):

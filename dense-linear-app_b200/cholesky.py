@@ -22,6 +22,7 @@ Nothing synchronises with the host between steps; LAPACK ``info`` is a device in
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import numpy as np
@@ -37,6 +38,12 @@ class TiledCholesky:
     trace = None
     tr = None
     thin_tasks = 0
+    _potrf_on_partition = False
+    s_potrf = None      # streams of the SM partition (chol_partition_create), None = no partition
+    s_rest = None
+    tail_tasks = 0
+    _part = None
+    _su = None          # the update stream of the step being enqueued (s_update or s_rest)
 
     def __init__(self, A: TileMatrix, group=None, lookahead: bool = True):
         self.A = A
@@ -93,6 +100,7 @@ class TiledCholesky:
         if self.cuda:
             self.s_update = torch.cuda.Stream(self.dev)
             self.s_panel = torch.cuda.Stream(self.dev, priority=-1)
+            self._make_partition()
             if self.tr is not None:
                 # one send stream per peer (copies to different peers run on different copy engines)
                 # and one for the credit words, so neither ever sits in front of a kernel
@@ -101,6 +109,41 @@ class TiledCholesky:
         else:
             self.s_update = self.s_panel = None
             self.s_sends, self.s_credit = {}, None
+
+    def _make_partition(self) -> None:
+        """SM partition for the tail of the factorization (include/chol_b200.h, chol_partition_create):
+        once the bulk of a step's update has at most `tail_tasks` tile tasks, the panel chain bounds the
+        step; from then on the updates run on the `rest` group of SMs and POTRF on its private group, so
+        none of its ~24 short dependent kernels waits for an update CTA to retire (measured on B200: a
+        POTRF tile takes 0.55 ms alone and 1.3-1.5 ms under a running update).  CHOL_PANEL_SMS=0 turns it
+        off; a driver without green contexts leaves the ordinary two-stream schedule."""
+        sms = int(os.environ.get("CHOL_PANEL_SMS", "16"))
+        self.tail_tasks = int(os.environ.get("CHOL_TAIL_TASKS", "28" if self.world == 1 else "48"))
+        if sms <= 0 or self.tail_tasks <= 0 or self.nt < 3:
+            return
+        key = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+        if key not in _partitions:
+            part = _lib.Partition()
+            try:
+                _lib.call("chol_partition_create", key, sms, C.byref(part))
+                _partitions[key] = (part, torch.cuda.ExternalStream(part.panel_stream, device=self.dev),
+                                    torch.cuda.ExternalStream(part.rest_stream, device=self.dev))
+            except _lib.CholError as e:
+                if os.environ.get("CHOL_PANEL_SMS"):
+                    raise
+                import sys
+                sys.stderr.write(f"[chol] no SM partition ({e}); using the two-stream schedule\n")
+                _partitions[key] = None
+        if _partitions[key] is not None:
+            self._part, self.s_potrf, self.s_rest = _partitions[key]
+            self.thin_tasks = 0           # the partition replaces the 1-CTA/SM tail updates
+
+    def _tail_start(self) -> int:
+        """First step from which every step's bulk update (part b) has at most tail_tasks tasks."""
+        k = self.nt
+        while k > 0 and self.step_tasks[k - 1][3] - self.step_tasks[k - 1][2] <= self.tail_tasks:
+            k -= 1
+        return k
 
     def _make_transport(self):
         """The peer-push transport of this geometry (tests substitute a shared-memory double)."""
@@ -135,9 +178,9 @@ class TiledCholesky:
             return
         # CUDA events on the launching stream around this one launch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(self.s_update)
+        e0.record(self._su or self.s_update)
         _lib.call("chol_gemm_tasks_ex", tasks_ptr, ntasks, b, b, b, b, b, b, -1.0, 1.0, occ, st)
-        e1.record(self.s_update)
+        e1.record(self._su or self.s_update)
         first = (tasks_ptr - self.d_tasks.data_ptr()) // 32
         nsyrk = int(self.tasks_host[first:first + ntasks, 3].sum()) if 0 <= first < len(self.tasks_host) else 0
         self.update_events.append((e0, e1, (2 * ntasks - nsyrk) * float(b) ** 3))
@@ -294,7 +337,21 @@ class TiledCholesky:
         kq, kp = k % g.Q, k % g.P
         in_col = kq == lay.q
         is_diag = in_col and kp == lay.p
-        if is_diag:
+        if is_diag and self._potrf_on_partition:
+            # POTRF on its private SMs: it keeps its place in the panel stream's order (everything enqueued
+            # there so far comes first, everything after it waits for it), only its kernels run elsewhere
+            sp = self.s_potrf
+            ev = torch.cuda.Event()
+            ev.record(self.s_panel)
+            sp.wait_event(ev)
+            with torch.cuda.stream(sp):
+                self._mark("potrf0", k, sp)
+                self._k_potrf(self.A.tile_ptr(k, k), k * self.b, self._stream_ptr(sp))
+                self._mark("potrf1", k, sp)
+                ev = torch.cuda.Event()
+                ev.record(sp)
+            self.s_panel.wait_event(ev)
+        elif is_diag:
             self._mark("potrf0", k, self.s_panel)
             self._k_potrf(self.A.tile_ptr(k, k), k * self.b, st)
             self._mark("potrf1", k, self.s_panel)
@@ -363,7 +420,21 @@ class TiledCholesky:
         ev_col = None      # column k has all its updates        -> TRSM(k) may start
         ns = self.nslots
         ev_upd = [None] * ns   # update k finished reading panel slot k % nslots
+        # SM partition (tail of a factorization only): steps >= k_sw update on the `rest` SMs, and the POTRFs
+        # that overlap those updates (steps > k_sw) run on the panel group
+        part = cuda and factor and self.lookahead and self.s_potrf is not None
+        k_sw = self._tail_start() if part else nt + 1
+        self._su = self.s_update
+        self._potrf_on_partition = False
+        if part and k_sw < nt:
+            self.s_rest.wait_stream(cur)
+            self.s_potrf.wait_stream(cur)
         for k in range(nt):
+            if part and k == k_sw:
+                self.s_rest.wait_stream(self.s_update)
+                self._su = self.s_rest
+            self._potrf_on_partition = part and k > k_sw
+            su = self._su
             # ---- panel k
             if cuda:
                 with torch.cuda.stream(self.s_panel):
@@ -379,7 +450,7 @@ class TiledCholesky:
                     self._panel_rest(k, factor)
                     ev_panel = torch.cuda.Event()
                     ev_panel.record(self.s_panel)
-                self.s_update.wait_event(ev_panel)
+                su.wait_event(ev_panel)
                 if tr is not None and (k % self.grid.Q) == self.lay.q:
                     # this rank's TRSM k is enqueued: the L_kk slot it read may be overwritten
                     self.s_credit.wait_event(ev_panel)
@@ -392,7 +463,7 @@ class TiledCholesky:
                 if tr is not None and (k % self.grid.Q) == self.lay.q:
                     tr.release_diag(k, 0)
             # ---- trailing update k
-            st = self._stream_ptr(self.s_update)
+            st = self._stream_ptr(su)
             if pre_update is not None:
                 pre_update(k, st)
             off, nd, na, ntot = self.step_tasks[k]
@@ -403,11 +474,11 @@ class TiledCholesky:
                 if tr is not None:
                     tr.release_panel(k, 0)
                 continue
-            with torch.cuda.stream(self.s_update):
+            with torch.cuda.stream(su):
                 gated = k == 0 and bool(step0_gates)
                 if gated:
                     for ev in (step0_gates if not self.lookahead else step0_gates[:1]):
-                        self.s_update.wait_event(ev)
+                        su.wait_event(ev)
                 if not self.lookahead:
                     if ntot:
                         self._k_update(base, ntot, st)
@@ -419,7 +490,7 @@ class TiledCholesky:
                 # A rank that owns nothing of a stage has nothing to wait for: it only receives, and may
                 # join the broadcasts as soon as its receive slot is free (ev_upd of step k-1).
                 ev_diag = ev_col = None
-                self._mark("upd0", k, self.s_update)
+                self._mark("upd0", k, su)
                 if nd:
                     self._k_update(base, nd, st)
                     ev_diag = self._record()
@@ -427,22 +498,27 @@ class TiledCholesky:
                     self._k_update(base + nd * 32, na - nd, st)
                 if na:
                     ev_col = self._record()
-                    self._mark("upd_a", k, self.s_update)
+                    self._mark("upd_a", k, su)
                 if gated:
                     # host-resident input: release part b group by group behind the upload
                     for g, (t0, t1, _, _) in enumerate(self.step0_groups):
-                        self.s_update.wait_event(step0_gates[1 + g])
+                        su.wait_event(step0_gates[1 + g])
                         self._k_update(base + (na + t0) * 32, t1 - t0, st)
                 elif ntot > na:
                     # the bulk of the update overlaps panel step k+1: once it is small enough for that panel
                     # chain to bound the step, it runs at one CTA per SM and leaves the chain's kernels room
                     self._k_update(base + na * 32, ntot - na, st, thin=0 < ntot - na <= self.thin_tasks)
                 ev_upd[k % ns] = self._record()
-                self._mark("upd1", k, self.s_update)
+                self._mark("upd1", k, su)
                 self._release_panel(k, ev_upd[k % ns])
         if cuda:
             cur.wait_stream(self.s_update)
             cur.wait_stream(self.s_panel)
+            if part and k_sw < nt:
+                cur.wait_stream(self.s_rest)
+                cur.wait_stream(self.s_potrf)
+            self._su = self.s_update
+            self._potrf_on_partition = False
             if tr is not None:
                 for s_ in self.s_sends.values():
                     cur.wait_stream(s_)
@@ -472,7 +548,7 @@ class TiledCholesky:
 
     def _record(self):
         ev = torch.cuda.Event()
-        ev.record(self.s_update)
+        ev.record(self._su or self.s_update)
         return ev
 
     def factor(self) -> None:
@@ -639,3 +715,4 @@ def potrf_tile_desc(uplo: str, A: TileMatrix, group=None, lookahead: bool = True
 
 
 _plans: dict = {}
+_partitions: dict = {}      # device index -> (chol_partition_t, panel stream, rest stream) | None, one per process

@@ -122,55 +122,102 @@ constexpr int BATCHED_LL_MAX_N = 256;
 template <int STAGES>
 struct BatchedLL {
     static constexpr int SLAB = BLK * BL_PITCH;
-    static constexpr size_t SMEM = size_t(STAGES * SLAB + BLW * BL_LP + BLW) * 8 + 2 * STAGES * 8 + 16;
+    static constexpr size_t SMEM = size_t(STAGES * SLAB + BLW * BL_LP + BLW + 2 * SB) * 8 + 2 * STAGES * 8 + 16;
 };
 
-// 1/sqrt(d) for a positive normal double: the hardware's 23-bit seed (MUFU.RSQ64H) refined by two
-// Newton steps, all inline — the library rsqrt() carries a slow path whose call spills the 32 row
-// registers of the factorization around every pivot.  ~1 ulp.
-__device__ __forceinline__ double rsqrt_pos(double d) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    const double h = 0.5 * d;
-    double e = fma(-h * r, r, 0.5);
-    r = fma(r, e, r);
-    e = fma(-h * r, r, 0.5);
-    return fma(r, e, r);
+// In-register Cholesky of a 32x32 block, lane = row (a[j] = element (lane, j), upper part ignored).
+// Returns the 1-based index of the first non-positive (or NaN) pivot, 0 if none; inv_out = 1 / l_cc of
+// this lane's own diagonal element.
+//
+// The 32 pivots are one dependent chain, and on B200 a dependent FP64 operation issues ~35 cycles after
+// its producer (measured with clock64(): the first version of this routine — pivot shuffle, rsqrt seed +
+// two Newton steps, scaling, column shuffle, update — cost 370 cycles per pivot, 11.8k per block, and a
+// variant that broadcast the column through shared memory instead of shuffles 410).  So the chain is kept
+// to five FP64 operations per pivot:
+//   * 1/sqrt(d): the hardware's 23-bit seed r0 (MUFU.RSQ64H) and ONE third-order correction
+//     e = 1/2 - (d/2) r0^2,  1/sqrt(d) = r0 (1 + e + 3/2 e^2 + O(e^3)),  |e| <= 2^-22 so the cubic term is
+//     below 2^-64 (1.2 units of 2^-53 in all, checked against 200-bit arithmetic);
+//   * the scaled column is formed directly as l = x0 + (x0 e)(1 + 3/2 e), x0 = a r0 — the separate
+//     multiplication by the refined reciprocal is gone (2.2 units of 2^-53);
+//   * every lane keeps its OWN diagonal element in `diag`, updated with its own l (no shuffle), so the next
+//     pivot is one shuffle behind the scaling instead of shuffle + fma + shuffle.
+// sqrt(d) for the diagonal and the refined reciprocal for inv_out are computed off the chain.
+//
+// The loop over the pivots is a REAL loop (four phases of eight steps, `#pragma unroll 1`): fully unrolled,
+// the compiler sinks every update of column j down to just before pivot j — the right-looking sweep turns
+// into a left-looking one whose column update is a serial chain of j dependent FMAs (SASS of the unrolled
+// form; 18.7k cycles per block).  To index registers statically inside a rolled loop the row is kept
+// ROTATING: w[0] is always the current column, and the update writes column j into slot j-1.  The results go
+// to `out` (column c of the factor at out[c * ldo], this lane's row) as they are produced; out may be
+// shared or global memory.  `bc` = 64 doubles of shared memory private to the calling warp.  The next
+// pivot's broadcast and rsqrt seed are issued before the row update.
+template <int LIVE>
+__device__ __forceinline__ void potrf32_phase(double (&w)[SB], double& diag, double& d, double& r0, int& info,
+                                              double& inv_out, const int c0, double* __restrict__ out, const int ldo, double* bc) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int cc = 0; cc < 8; ++cc) {
+        const int c = c0 + cc;
+        if (!(d > 0.0) && info == 0) info = c + 1;
+        const double e = fma(-(0.5 * d) * r0, r0, 0.5);
+        const double v = fma(1.5, e, 1.0);
+        const double x0 = w[0] * r0;
+        const double l = fma(x0 * e, v, x0);              // on lane c: d / sqrt(d), unused by the others
+        diag = fma(-l, l, diag);                          // lanes > c; lane c's own pivot is consumed
+        const double dn = __shfl_sync(0xffffffffu, diag, (c + 1) & 31);
+        double rn;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rn) : "d"(dn));
+        {
+            // off the chain: the refined reciprocal, and sqrt(d) to < 1 ulp for the diagonal element
+            const double inv = fma(r0 * e, v, r0);
+            const double piv = d * inv;
+            const double root = fma(fma(-piv, piv, d), 0.5 * inv, piv);
+            if (lane >= c) out[size_t(c) * ldo] = (lane == c) ? root : l;
+            if (lane == c) inv_out = inv;
+        }
+        // row update, rotating: new w[j-1] = old w[j] - l * l_{c+j}.  The column reaches the other lanes through
+        // shared memory (one STS, broadcast LDS): a single warp gets one SHFL through about every 11 cycles
+        // (measured: 370 cycles per pivot with 2 x (31 - c) shuffles, whatever the length of the FP64 chain),
+        // so shuffles carry only the pivot.  Two buffers: a lane may still be reading step c-1's column when
+        // another one, past the __syncwarp of step c, writes step c+1's.
+        double* col = bc + (c & 1) * SB;
+        col[lane] = l;
+        __syncwarp();
+#pragma unroll
+        for (int j = 1; j < LIVE; ++j) w[j - 1] = fma(-l, col[(c + j) & 31], w[j]);
+        d = dn;
+        r0 = rn;
+    }
 }
 
-// In-register Cholesky of a 32x32 block, lane = row (a[j] = element (lane, j), upper part ignored).
-// Pivot through rsqrt_pos: 1/piv = rsqrt(d) feeds the column scaling, piv = d * rsqrt(d) (+ one
-// correction) only the diagonal — no square root and no division on the dependent chain.  Returns the 1-based index of the first
-// non-positive (or NaN) pivot, 0 if none; inv_out = 1 / l_cc of this lane's own diagonal element.
-__device__ __forceinline__ int potrf32_regs(double (&a)[SB], double& inv_out) {
+// a[j] = element (lane, j) on entry (upper part ignored); the factor is written to out / ldo (lower part only:
+// lane >= column); bc = 64 doubles of shared scratch owned by this warp.  Returns info (first bad pivot, 1-based, 0 = none); inv_out = 1 / l_cc of this lane's own row.
+__device__ __forceinline__ int potrf32_regs(double (&a)[SB], double& inv_out, double* __restrict__ out, const int ldo,
+                                            double* bc) {
     const int lane = threadIdx.x & 31;
     int info = 0;
     inv_out = 0.0;
+    double diag = 0.0;
 #pragma unroll
-    for (int c = 0; c < SB; ++c) {
-        const double d = __shfl_sync(0xffffffffu, a[c], c);
-        if (!(d > 0.0) && info == 0) info = c + 1;
-        const double inv = rsqrt_pos(d);
-        double piv = d * inv;
-        piv = fma(fma(-piv, piv, d), 0.5 * inv, piv);     // off the dependent chain: sqrt(d) to < 1 ulp
-        const double l = (lane == c) ? piv : a[c] * inv;
-        a[c] = l;
-        if (lane == c) inv_out = inv;
-        // the broadcasts of l_jc are issued eight at a time ahead of the FMAs that use them: a shuffle
-        // directly in front of its FMA exposes the full shuffle latency 496 times (ncu: 12 us per block)
-#pragma unroll
-        for (int j0 = c + 1; j0 < SB; j0 += 8) {
-            double lj[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (j0 + u < SB) lj[u] = __shfl_sync(0xffffffffu, l, j0 + u);
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (j0 + u < SB) a[j0 + u] = fma(-l, lj[u], a[j0 + u]);
-        }
-    }
+    for (int c = 0; c < SB; ++c)
+        if (lane == c) diag = a[c];
+    double d = __shfl_sync(0xffffffffu, diag, 0);
+    double r0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    // columns beyond the block (wrapped lanes of the last steps' shuffles) only ever reach dead slots
+    potrf32_phase<32>(a, diag, d, r0, info, inv_out, 0, out, ldo, bc);
+    potrf32_phase<24>(a, diag, d, r0, info, inv_out, 8, out, ldo, bc);
+    potrf32_phase<16>(a, diag, d, r0, info, inv_out, 16, out, ldo, bc);
+    potrf32_phase<8>(a, diag, d, r0, info, inv_out, 24, out, ldo, bc);
     return info;
 }
+
+#ifdef CHOL_DIAG_CLOCKS   // debug builds only (tools/): phase timestamps of one CTA of the last batched launch
+__device__ long long g_bat_clk[64];
+#define BL_CLK(i) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x / 2) g_bat_clk[i] = clock64(); } while (0)
+#else
+#define BL_CLK(i) do { } while (0)
+#endif
 
 template <int STAGES, int MIN_CTAS>
 __global__ void __launch_bounds__(BL_THREADS, MIN_CTAS)
@@ -180,7 +227,8 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
     double* slabs = reinterpret_cast<double*>(smem_dyn);
     double* Lcm = slabs + STAGES * SLAB;           // L_jj, column-major, pitch BL_LP
     double* invd = Lcm + BLW * BL_LP;              // 1 / l_cc
-    uint64_t* bars = reinterpret_cast<uint64_t*>(invd + BLW);   // [0,STAGES) full, [STAGES,2*STAGES) empty
+    double* bcast = invd + BLW;                    // potrf32_regs' column buffers (warp 0)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bcast + 2 * SB);   // [0,STAGES) full, [STAGES,2*STAGES) empty
     __shared__ int s_info;
 
     double* A = Abase + size_t(blockIdx.x) * size_t(stride);
@@ -201,6 +249,7 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
 
     int it = 0;                                     // slabs streamed so far (same count in every warp)
     const int nb = n / BLW;
+    BL_CLK(0);
     for (int j = 0; j < nb; ++j) {
         const int r0 = j * BLW;
         const int R = n - r0;
@@ -345,6 +394,7 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
             run_pass(0);
             __syncthreads();    // the updated diagonal block (pass 0, block 0) is visible to warp 0
         }
+        BL_CLK(1 + 3 * j);
         // ---- diagonal block: one warp, registers + shuffles; the others finish the update meanwhile
         if (warp != 0) {
             if (two) run_pass(1);
@@ -355,17 +405,18 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
 #pragma unroll
             for (int c = 0; c < SB; ++c) a[c] = (lane >= c) ? gD[size_t(c) * lda] : 0.0;
             double inv;
-            const int info = potrf32_regs(a, inv);
+            // the factor goes to the shared copy L_jj (for the solve below), then from there to global memory
+            const int info = potrf32_regs(a, inv, Lcm + lane, BL_LP, bcast);
             if (info != 0 && lane == 0 && s_info == 0) s_info = r0 + info;
+            __syncwarp();
             double* gDw = A + size_t(r0) * lda + r0 + lane;
 #pragma unroll
-            for (int c = 0; c < SB; ++c) {
-                if (lane >= c) gDw[size_t(c) * lda] = a[c];
-                Lcm[c * BL_LP + lane] = a[c];
-            }
+            for (int c = 0; c < SB; ++c)
+                if (lane >= c) gDw[size_t(c) * lda] = Lcm[c * BL_LP + lane];
             invd[lane] = inv;
         }
         __syncthreads();
+        BL_CLK(2 + 3 * j);
         // ---- rows below: X L_jj^T = C by forward substitution, one thread per row
         for (int row = r0 + BLW + tid; row < n; row += BL_THREADS) {
             // compiler barrier: without it the (loop-invariant) shared-memory loads of L_jj are hoisted
@@ -394,6 +445,7 @@ potrf_batched_ll_kernel(int n, double* __restrict__ Abase, int lda, long long st
         // the next block column's TMA reads (async proxy) must see these generic-proxy writes
         asm volatile("fence.proxy.async;" ::: "memory");
         __syncthreads();
+        BL_CLK(3 + 3 * j);
     }
     if (tid == 0) d_info[blockIdx.x] = s_info;
 }

@@ -538,4 +538,16 @@ int chol_fp64_peak(int kind, int iters, double* flops_out, void* stream) {
     return 0;
 }
 
+#ifdef CHOL_DIAG_CLOCKS
+// debug builds only: phase timestamps (SM clock) of the most recent potrf_diag32_kernel launch
+int chol_debug_diag_clocks(long long* out16) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_diag_clk, 16 * sizeof(long long));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "chol_debug_diag_clocks");
+}
+int chol_debug_batched_clocks(long long* out32) {
+    cudaError_t e = cudaMemcpyFromSymbol(out32, g_bat_clk, 32 * sizeof(long long));
+    return e == cudaSuccess ? 0 : fail_cuda(e, "chol_debug_batched_clocks");
+}
+#endif
+
 }  // extern "C"

@@ -28,7 +28,14 @@ constexpr int D2_THREADS = 256;
 constexpr int D2_BP = 36;                         // pitch of a packed 32x32 block: == 4 (mod 16) doubles
 constexpr int D2_BLK = SB * D2_BP;                // doubles per block
 constexpr int D2_NBLK = 10;                       // lower blocks of a 4x4 block matrix
-constexpr size_t D2_SMEM = size_t(D2_NBLK * D2_BLK + NBD) * 8 + 16;
+constexpr size_t D2_SMEM = size_t(D2_NBLK * D2_BLK + NBD + 2 * SB) * 8 + 16;
+
+#ifdef CHOL_DIAG_CLOCKS   // debug builds only (tools/): phase timestamps of the last diag32 launch
+__device__ long long g_diag_clk[64];
+#define D2_CLK(i) do { if (threadIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define D2_CLK(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ int d2_blk(int I, int J) { return I * (I + 1) / 2 + J; }   // I >= J
 
@@ -40,43 +47,39 @@ potrf_diag32_kernel(int n, double* __restrict__ A, int lda, double* __restrict__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* S = reinterpret_cast<double*>(smem_raw);
     double* invd = S + D2_NBLK * D2_BLK;
+    double* bcast = invd + NBD;                     // potrf32_regs' column buffers (warp 0)
     __shared__ int s_info;
+    __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g = lane >> 2, t = lane & 3;
     const int nb = n / SB;
     if (tid == 0) s_info = 0;
-    // ---- load the lower blocks: thread -> (row r = tid % 32, columns c0, c0 + 8, ...); the global
-    // loads of five blocks are in flight together (one block at a time costs ten serialized L2 trips)
+    D2_CLK(0);
+    // ---- load the lower blocks with the TMA engine: one 256-byte bulk copy per block column (a column of a
+    // packed block is contiguous in both memories), all in flight at once, completion on one mbarrier.
+    // (The per-thread loads this replaces took 4.4k cycles, two serialized L2 round trips.)  The strict upper
+    // triangle of the diagonal blocks comes along and is ignored.
     {
-        const int r = tid & 31, c0 = tid >> 5;
-        const int nblocks = nb * (nb + 1) / 2;
-        for (int b0 = 0; b0 < nblocks; b0 += 5) {
-            double v[5][4];
-#pragma unroll
-            for (int w = 0; w < 5; ++w) {
-                const int bi = b0 + w;
-                if (bi < nblocks) {
-                    int I = 0;
-                    while ((I + 1) * (I + 2) / 2 <= bi) ++I;
-                    const int J = bi - I * (I + 1) / 2;
-                    const double* src = A + size_t(J * SB) * lda + I * SB + r;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) v[w][u] = src[size_t(c0 + 8 * u) * lda];
-                }
-            }
-#pragma unroll
-            for (int w = 0; w < 5; ++w) {
-                const int bi = b0 + w;
-                if (bi < nblocks) {
-                    double* blk = S + bi * D2_BLK;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) blk[(c0 + 8 * u) * D2_BP + r] = v[w][u];
-                }
-            }
+        const uint32_t bar = smem_u32(&s_bar);
+        const int ncols = nb * (nb + 1) / 2 * SB;
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar, uint32_t(ncols) * uint32_t(SB * 8));
         }
+        __syncthreads();
+        for (int idx = tid; idx < ncols; idx += D2_THREADS) {
+            const int bi = idx >> 5, c = idx & 31;
+            int I = 0;
+            while ((I + 1) * (I + 2) / 2 <= bi) ++I;
+            const int J = bi - I * (I + 1) / 2;
+            bulk_g2s(smem_u32(S + bi * D2_BLK + c * D2_BP), A + size_t(J * SB + c) * lda + I * SB, SB * 8, bar);
+        }
+        mbar_wait(bar, 0);
     }
     __syncthreads();
+    D2_CLK(1);
     for (int J = 0; J < nb; ++J) {
         double* LJJ = S + d2_blk(J, J) * D2_BLK;
         if (warp == 0) {
@@ -84,13 +87,13 @@ potrf_diag32_kernel(int n, double* __restrict__ A, int lda, double* __restrict__
 #pragma unroll
             for (int c = 0; c < SB; ++c) a[c] = (lane >= c) ? LJJ[c * D2_BP + lane] : 0.0;
             double inv;
-            const int info = potrf32_regs(a, inv);
+            // (only the lower part of L_JJ is written, and nothing reads the strict upper part)
+            const int info = potrf32_regs(a, inv, LJJ + lane, D2_BP, bcast);
             if (info != 0 && lane == 0 && s_info == 0) s_info = J * SB + info;
-#pragma unroll
-            for (int c = 0; c < SB; ++c) LJJ[c * D2_BP + lane] = a[c];     // upper part: zero
             invd[J * SB + lane] = inv;
         }
         __syncthreads();
+        D2_CLK(2 + 3 * J);
         const int R = (nb - 1 - J) * SB;           // rows below: 0, 32, 64 or 96
         if (tid < R) {
             // ---- forward substitution, one thread per row of the blocks (I, J), I > J
@@ -136,85 +139,83 @@ potrf_diag32_kernel(int n, double* __restrict__ A, int lda, double* __restrict__
         }
         if (R == 0) break;
         __syncthreads();
-        // ---- trailing update on the DMMA pipe: block (I, K) -= X_I X_K^T, J < K <= I, one warp each
+        D2_CLK(3 + 3 * J);
+        // ---- trailing update on the DMMA pipe: block (I, K) -= X_I X_K^T, J < K <= I, cut into 16 x 16
+        // quarters dealt round-robin to the 8 warps.  (One warp per 32 x 32 block left the DMMA pipe of two
+        // of the four sub-partitions with two blocks and the others with one or none: 8.5k / 6.2k / 5.5k
+        // cycles for 6 / 3 / 1 blocks; a quarter is 32 DMMAs = 512 pipe cycles.)  Same products, same
+        // order of accumulation per element as the whole-block form.
         {
-            const int m = nb - 1 - J;              // 1..3 -> m (m + 1) / 2 <= 6 block tasks
-            int I = -1, K = -1;
-            if (warp < m * (m + 1) / 2) {
+            const int m = nb - 1 - J;              // 1..3 -> m (m + 1) / 2 <= 6 blocks
+            const int nq = 2 * m * (m + 1);
+            for (int qt = warp; qt < nq; qt += D2_THREADS / 32) {
+                const int task = qt >> 2, q = (qt >> 1) & 1, r = qt & 1;
                 int ti = 0;
-                while ((ti + 1) * (ti + 2) / 2 <= warp) ++ti;
-                I = J + 1 + ti;
-                K = J + 1 + (warp - ti * (ti + 1) / 2);
-            }
-            if (I >= 0) {
-                const double* XI = S + d2_blk(I, J) * D2_BLK + t * D2_BP + 2 * g;
-                const double* XK = S + d2_blk(K, J) * D2_BLK + t * D2_BP + 2 * g;
-                double* C = S + d2_blk(I, K) * D2_BLK;
-                double acc[2][2][2][2][2];
+                while ((ti + 1) * (ti + 2) / 2 <= task) ++ti;
+                const int I = J + 1 + ti, K = J + 1 + (task - ti * (ti + 1) / 2);
+                if (I == K && q == 0 && r == 1) continue;      // strict upper quarter of a diagonal block: never read
+                const double* XI = S + d2_blk(I, J) * D2_BLK + t * D2_BP + q * 16 + 2 * g;
+                const double* XK = S + d2_blk(K, J) * D2_BLK + t * D2_BP + r * 16 + 2 * g;
+                double* C = S + d2_blk(I, K) * D2_BLK + (r * 16 + 4 * t) * D2_BP + q * 16 + 2 * g;
+                double acc[2][2][2];               // [mp][np][e]
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+                for (int e = 0; e < 2; ++e)
 #pragma unroll
-                    for (int r = 0; r < 2; ++r)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-#pragma unroll
-                            for (int np = 0; np < 2; ++np) {
-                                const double2 v = *reinterpret_cast<const double2*>(
-                                    C + (r * 16 + 4 * t + 2 * e + np) * D2_BP + q * 16 + 2 * g);
-                                acc[q][r][0][np][e] = v.x;
-                                acc[q][r][1][np][e] = v.y;
-                            }
-#pragma unroll
-                for (int kk = 0; kk < SB; kk += 4) {
-                    double2 a[2], b[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) a[q] = *reinterpret_cast<const double2*>(XI + kk * D2_BP + q * 16);
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        b[r] = *reinterpret_cast<const double2*>(XK + kk * D2_BP + r * 16);
-                        b[r].x = -b[r].x;
-                        b[r].y = -b[r].y;
+                    for (int np = 0; np < 2; ++np) {
+                        const double2 v = *reinterpret_cast<const double2*>(C + (2 * e + np) * D2_BP);
+                        acc[0][np][e] = v.x;
+                        acc[1][np][e] = v.y;
                     }
 #pragma unroll
-                    for (int q = 0; q < 2; ++q)
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            dmma884(acc[q][r][0][0][0], acc[q][r][0][0][1], a[q].x, b[r].x);
-                            dmma884(acc[q][r][0][1][0], acc[q][r][0][1][1], a[q].x, b[r].y);
-                            dmma884(acc[q][r][1][0][0], acc[q][r][1][0][1], a[q].y, b[r].x);
-                            dmma884(acc[q][r][1][1][0], acc[q][r][1][1][1], a[q].y, b[r].y);
-                        }
+                for (int kk = 0; kk < SB; kk += 4) {
+                    const double2 a = *reinterpret_cast<const double2*>(XI + kk * D2_BP);
+                    double2 b = *reinterpret_cast<const double2*>(XK + kk * D2_BP);
+                    b.x = -b.x;
+                    b.y = -b.y;
+                    dmma884(acc[0][0][0], acc[0][0][1], a.x, b.x);
+                    dmma884(acc[0][1][0], acc[0][1][1], a.x, b.y);
+                    dmma884(acc[1][0][0], acc[1][0][1], a.y, b.x);
+                    dmma884(acc[1][1][0], acc[1][1][1], a.y, b.y);
                 }
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+                for (int e = 0; e < 2; ++e)
 #pragma unroll
-                    for (int r = 0; r < 2; ++r)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-#pragma unroll
-                            for (int np = 0; np < 2; ++np)
-                                *reinterpret_cast<double2*>(C + (r * 16 + 4 * t + 2 * e + np) * D2_BP + q * 16 + 2 * g) =
-                                    make_double2(acc[q][r][0][np][e], acc[q][r][1][np][e]);
+                    for (int np = 0; np < 2; ++np)
+                        *reinterpret_cast<double2*>(C + (2 * e + np) * D2_BP) = make_double2(acc[0][np][e], acc[1][np][e]);
             }
         }
         __syncthreads();
+        D2_CLK(4 + 3 * J);
     }
     __syncthreads();
+    D2_CLK(14);
     if (s_info != 0 && tid == 0 && d_info) atomicCAS(d_info, 0, info_base + s_info);
-    // ---- store L: lower triangle only
+    // ---- store L, lower triangle only, with bulk copies shared memory -> global: a whole column of an
+    // off-diagonal block, rows c.. of column c of a diagonal block (from an even row: 16-byte alignment;
+    // the diagonal element of an odd column goes out as a plain store).  The per-thread LDS + STG loop this
+    // replaces took 8k cycles.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the blocks were written through the generic proxy
+    __syncthreads();
     {
-        const int r = tid & 31, c0 = tid >> 5;
-        for (int I = 0; I < nb; ++I)
-            for (int J = 0; J <= I; ++J) {
-                const double* blk = S + d2_blk(I, J) * D2_BLK;
-                double* dst = A + size_t(J * SB) * lda + I * SB + r;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c = c0 + 8 * u;
-                    if (I > J || r >= c) dst[size_t(c) * lda] = blk[c * D2_BP + r];
-                }
+        const int ncols = nb * (nb + 1) / 2 * SB;
+        for (int idx = tid; idx < ncols; idx += D2_THREADS) {
+            const int bi = idx >> 5, c = idx & 31;
+            int I = 0;
+            while ((I + 1) * (I + 2) / 2 <= bi) ++I;
+            const int J = bi - I * (I + 1) / 2;
+            const double* src = S + bi * D2_BLK + c * D2_BP;
+            double* dst = A + size_t(J * SB + c) * lda + I * SB;
+            int r0 = 0;
+            if (I == J) {
+                r0 = (c + 1) & ~1;                                 // first even row >= c
+                if (r0 != c) dst[c] = src[c];
             }
+            if (r0 < SB) bulk_s2g(dst + r0, smem_u32(src + r0), uint32_t(SB - r0) * 8u);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+    D2_CLK(15);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -80,6 +80,27 @@ int wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t st) {
 
 }  // namespace
 
+// ---- SM partition for the panel chain (green contexts) -----------------------------------------
+namespace {
+
+struct Partition {
+    CUgreenCtx panel_ctx = nullptr, rest_ctx = nullptr;
+    CUstream panel_stream = nullptr, rest_stream = nullptr;
+};
+
+template <class F>
+bool entry(const char* name, F& fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q);
+    (void)cudaGetLastError();
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return false;
+    fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+}  // namespace
+
 extern "C" {
 
 int chol_peer_alloc(size_t bytes, void** out) {
@@ -209,6 +230,81 @@ int chol_flag_post(uint32_t* const* flags, int n, uint32_t value, void* stream) 
         fp.dst[i] = flags[i];
     }
     return post_flags(fp, (cudaStream_t)stream);
+}
+
+int chol_partition_create(int device, int min_panel_sms, chol_partition_t* out) {
+    if (!out) return fail_arg(3, "chol_partition_create", "out");
+    memset(out, 0, sizeof(*out));
+    if (min_panel_sms <= 0) return fail_arg(2, "chol_partition_create", "min_panel_sms");
+    if (int rc = ensure_init()) return rc;
+    CUresult (*p_devget)(CUdevice*, int) = nullptr;
+    CUresult (*p_getres)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+    CUresult (*p_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int,
+                        unsigned int) = nullptr;
+    CUresult (*p_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+    CUresult (*p_gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*p_gdestroy)(CUgreenCtx) = nullptr;
+    CUresult (*p_gstream)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+    if (!entry("cuDeviceGet", p_devget) || !entry("cuDeviceGetDevResource", p_getres) ||
+        !entry("cuDevSmResourceSplitByCount", p_split) || !entry("cuDevResourceGenerateDesc", p_desc) ||
+        !entry("cuGreenCtxCreate", p_gcreate) || !entry("cuGreenCtxDestroy", p_gdestroy) ||
+        !entry("cuGreenCtxStreamCreate", p_gstream)) {
+        g_err = "chol_partition_create: this driver has no green-context entry points";
+        return 1;
+    }
+    CUdevice dev;
+    CUresult r = p_devget(&dev, device);
+    if (r != CUDA_SUCCESS) return fail_cu(r, "cuDeviceGet");
+    CUdevResource all, grp, rest;
+    r = p_getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM);
+    if (r != CUDA_SUCCESS) return fail_cu(r, "cuDeviceGetDevResource");
+    unsigned int ngroups = 1;
+    r = p_split(&grp, &ngroups, &all, &rest, 0, (unsigned int)min_panel_sms);
+    if (r != CUDA_SUCCESS) return fail_cu(r, "cuDevSmResourceSplitByCount");
+    if (ngroups != 1 || grp.sm.smCount == 0 || rest.sm.smCount == 0) {
+        g_err = "chol_partition_create: the device's SMs cannot be split that way";
+        return 1;
+    }
+    Partition* P = new Partition;
+    CUdevResourceDesc d1 = nullptr, d2 = nullptr;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    do {
+        if ((r = p_desc(&d1, &grp, 1)) != CUDA_SUCCESS) break;
+        if ((r = p_desc(&d2, &rest, 1)) != CUDA_SUCCESS) break;
+        if ((r = p_gcreate(&P->panel_ctx, d1, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) break;
+        if ((r = p_gcreate(&P->rest_ctx, d2, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) break;
+        if ((r = p_gstream(&P->panel_stream, P->panel_ctx, CU_STREAM_NON_BLOCKING, prio_hi)) != CUDA_SUCCESS) break;
+        if ((r = p_gstream(&P->rest_stream, P->rest_ctx, CU_STREAM_NON_BLOCKING, prio_lo)) != CUDA_SUCCESS) break;
+    } while (0);
+    if (r != CUDA_SUCCESS) {
+        if (P->panel_stream) cudaStreamDestroy((cudaStream_t)P->panel_stream);
+        if (P->rest_stream) cudaStreamDestroy((cudaStream_t)P->rest_stream);
+        if (P->panel_ctx) p_gdestroy(P->panel_ctx);
+        if (P->rest_ctx) p_gdestroy(P->rest_ctx);
+        delete P;
+        return fail_cu(r, "chol_partition_create (green context setup)");
+    }
+    out->handle = P;
+    out->panel_stream = P->panel_stream;
+    out->rest_stream = P->rest_stream;
+    out->panel_sms = (int)grp.sm.smCount;
+    out->rest_sms = (int)rest.sm.smCount;
+    return 0;
+}
+
+int chol_partition_destroy(void* handle) {
+    if (!handle) return 0;
+    Partition* P = static_cast<Partition*>(handle);
+    CUresult (*p_gdestroy)(CUgreenCtx) = nullptr;
+    if (P->panel_stream) cudaStreamDestroy((cudaStream_t)P->panel_stream);
+    if (P->rest_stream) cudaStreamDestroy((cudaStream_t)P->rest_stream);
+    if (entry("cuGreenCtxDestroy", p_gdestroy)) {
+        if (P->panel_ctx) p_gdestroy(P->panel_ctx);
+        if (P->rest_ctx) p_gdestroy(P->rest_ctx);
+    }
+    delete P;
+    return 0;
 }
 
 }  // extern "C"

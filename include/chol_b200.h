@@ -208,6 +208,26 @@ int chol_tile_abs_sums(int m, int n, const double* A, int lda, int mode, double*
 /* B <- lower triangle of A, strict upper zeroed (dlacpy(ChamLower), V6:77). */
 int chol_tile_tril(int n, const double* A, int lda, double* B, int ldb, void* stream);
 
+/* ---- SM partition for the latency-critical panel chain -------------------------------- */
+
+/* The reference hands POTRF to a CPU worker and the updates to the CUDA worker (StarPU: no GPU codelet
+ * for POTRF, W2:238 / SURVEY 8a row a2), so its panel chain never queues behind GEMM tiles.  Here both
+ * run on one B200: while a trailing update fills every SM, each of the ~24 short kernels of a POTRF tile
+ * waits for an update CTA to retire (measured: 0.55 ms alone, 1.3-1.5 ms under the update).  This call
+ * splits the SMs with CUDA green contexts: `panel_stream` runs its kernels only on a private group of
+ * >= min_panel_sms SMs (rounded up to the hardware granularity, 8 on sm_100), `rest_stream` only on the
+ * remaining ones; both interoperate with ordinary streams and events.  The whole-matrix driver uses the
+ * pair for the last steps of a factorization, where the panel chain, not the update, bounds the step.
+ * Returns non-zero (and leaves *out zeroed) when the driver cannot provide such a split. */
+typedef struct chol_partition {
+    void* handle;        /* for chol_partition_destroy */
+    void* panel_stream;  /* cudaStream_t */
+    void* rest_stream;   /* cudaStream_t */
+    int panel_sms, rest_sms;
+} chol_partition_t;
+int chol_partition_create(int device, int min_panel_sms, chol_partition_t* out);
+int chol_partition_destroy(void* handle);
+
 /* ---- microbenchmarks for the roofline denominators -------------------------------- */
 
 /* kind 0: DFMA chains, 1: DMMA m8n8k4 chains on 8 warps per SM, 2: same on 4 warps.  Runs `iters` inner iterations on every

@@ -73,7 +73,7 @@ def fake_stream_ctx(s):
 class Probe(TiledCholesky):
     """One rank's schedule with recorded operations instead of kernels and collectives."""
 
-    def __init__(self, A, lookahead):
+    def __init__(self, A, lookahead, partition_tail=0):
         self.A, self.nt, self.b = A, A.nt, A.b
         self.grid, self.rank, self.lay = A.grid, A.rank, A.layout
         self.dev, self.world = A.device, A.grid.size
@@ -90,6 +90,10 @@ class Probe(TiledCholesky):
         self._build_plan()
         self.s_update, self.s_panel = FakeStream(), FakeStream()
         self.streams = {s.cuda_stream: s for s in (self.s_update, self.s_panel)}
+        if partition_tail:
+            # the SM partition of the tail (chol_partition_create): two more streams
+            self.s_potrf, self.s_rest, self.tail_tasks = FakeStream(), FakeStream(), partition_tail
+            self.streams.update({s.cuda_stream: s for s in (self.s_potrf, self.s_rest)})
         self.ops = []
         self.extra = {}                       # other tensors (residual scratch): data_ptr -> (name, tensor)
 
@@ -203,6 +207,27 @@ def test_factor_schedule_has_no_races(fake_cuda, P, Q, rank, lookahead):
         upd = [o for o in pr.ops if o[0] == "update"]
         pot = [o for o in pr.ops if o[0] == "potrf"]
         assert not happens_before(upd[2], pot[1]) and happens_before(upd[0], pot[1])
+
+
+@pytest.mark.parametrize("P,Q,rank", GRIDS)
+@pytest.mark.parametrize("tail", [3, 10, 1000])
+def test_partitioned_tail_schedule_has_no_races(fake_cuda, P, Q, rank, tail):
+    """With the SM partition the last steps' updates run on the `rest` stream and their POTRFs on the panel
+    group's stream (tail=1000: from step 0 on): same dependences, two more streams."""
+    N, b = 16 * 11, 16
+    M = TileMatrix(TileDesc(b, b, b * b, N, N, 0, 0, N, N, P, Q), rank, "cpu")
+    pr = Probe(M, True, partition_tail=tail)
+    pr._run(pr.d_tasks.data_ptr(), factor=True)
+    assert check_no_races(pr.ops) == []
+    used = {o[1] for o in pr.ops}
+    assert pr.s_rest.name in used or pr._tail_start() >= pr.nt
+    if P * Q == 1:
+        pot = [o for o in pr.ops if o[0] == "potrf"]
+        assert any(o[1] == pr.s_potrf.name for o in pot) and pot[0][1] == pr.s_panel.name
+        # still a lookahead: a partition POTRF is not ordered after the bulk update it overlaps
+        k = next(i for i, o in enumerate(pot) if o[1] == pr.s_potrf.name)
+        bulk = [o for o in pr.ops if o[0] == "update" and o[1] == pr.s_rest.name]
+        assert any(not happens_before(u, pot[k]) for u in bulk)
 
 
 @pytest.mark.parametrize("P,Q,rank", GRIDS)
