@@ -110,6 +110,15 @@ potrf_batched_global_kernel(int n, double* __restrict__ Abase, int lda, long lon
 //      none), written straight back to global memory.
 // The matrix never has to fit in shared memory; HBM sees each lower-triangle element once in and
 // once out (8 n (n+1) bytes per matrix = the algorithmic minimum), the re-reads of L hit L2.
+//
+// Measured on B200 with clock64() (one CTA of the four on an SM, 10 000 x 256, cycles per matrix): update
+// 230k, potrf32 + second pass 190k, substitution 100k; the FP64/DMMA pipe is busy 36 % of the time, the rest
+// is CTAs waiting at their own phase boundaries.  A variant with LOOKAHEAD inside the CTA (warps 1-3 already
+// update block column j+1 by the columns < j while warp 0 factors block (j, j); every block of C visited
+// twice, bit-identical results) was built and measured: faster for a single matrix (n = 224: 135 against
+// 145 us) but slower at the full batch (5.14 against 4.73 ms) — the second visit re-streams the B rows and
+// re-reads/re-writes C, and under four co-resident CTAs that extra L2 traffic costs more than the overlap
+// gains.  Dropped; what would help is more matrices in flight per SM (no dedicated producer warp).
 constexpr int BLW = 32;                 // block-column width
 constexpr int BLK = 8;                  // slab depth
 constexpr int BL_ROWS = 128;            // rows per pass

@@ -281,26 +281,31 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait(smem_u32(&bars[s]), ph);
         const double* st = smem + size_t(s) * STAGE_DOUBLES;
         const int kc = min(BK, p.k - it * BK);
+        // one k4 step: 6 LDS.128 feed 32 DMMAs
+        auto k4_step = [&](const int kk) {
+            double2 a[4], b[2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                a[q] = *reinterpret_cast<const double2*>(st + a_off + kk * PITCH + q * 16);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                b[r] = *reinterpret_cast<const double2*>(st + b_off + kk * PITCH_B + r * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    dmma884(acc[q][r][0][0][0], acc[q][r][0][0][1], a[q].x, b[r].x);
+                    dmma884(acc[q][r][0][1][0], acc[q][r][0][1][1], a[q].x, b[r].y);
+                    dmma884(acc[q][r][1][0][0], acc[q][r][1][0][1], a[q].y, b[r].x);
+                    dmma884(acc[q][r][1][1][0], acc[q][r][1][1][1], a[q].y, b[r].y);
+                }
+        };
+        // (Specialising full slabs into one branch-free basic block, so that ptxas schedules the fragment loads of
+        // a step under the DMMAs of the step before, was measured on B200: 34.27 against 34.38 TFLOP/s for this
+        // form at 120 tasks, 34.93 / 34.94 at 820 — the co-resident CTA already fills those bubbles.)
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
-            if (kk < kc) {
-                double2 a[4], b[2];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    a[q] = *reinterpret_cast<const double2*>(st + a_off + kk * PITCH + q * 16);
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-                    b[r] = *reinterpret_cast<const double2*>(st + b_off + kk * PITCH_B + r * 16);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        dmma884(acc[q][r][0][0][0], acc[q][r][0][0][1], a[q].x, b[r].x);
-                        dmma884(acc[q][r][0][1][0], acc[q][r][0][1][1], a[q].x, b[r].y);
-                        dmma884(acc[q][r][1][0][0], acc[q][r][1][0][1], a[q].y, b[r].x);
-                        dmma884(acc[q][r][1][1][0], acc[q][r][1][1][1], a[q].y, b[r].y);
-                    }
-            }
+            if (kk < kc) k4_step(kk);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars[STAGES + s]));
