@@ -43,6 +43,7 @@ SIGNATURES = {
     "chol_tile_sumsq": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "chol_tile_abs_sums": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "chol_tile_tril": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "chol_tile_transpose": (c_int, [c_int, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "chol_fp64_peak": (c_int, [c_int, c_int, C.POINTER(c_double), c_void_p]),
 }
 

@@ -696,11 +696,23 @@ def _norms(M: TileMatrix, ch: TiledCholesky) -> tuple[float, float]:
 
 
 def potrf_tile_desc(uplo: str, A: TileMatrix, group=None, lookahead: bool = True) -> int:
-    """int CHAMELEON_dpotrf_Tile(cham_uplo_t uplo, CHAM_desc_t *A) (v6_test.c:56): in-place lower
-    Cholesky of the tiled SPD matrix; returns LAPACK info.  Only uplo = 'L' (ChamLower) — the one
-    the reference calls."""
+    """int CHAMELEON_dpotrf_Tile(cham_uplo_t uplo, CHAM_desc_t *A) (v6_test.c:56): in-place Cholesky of
+    the tiled SPD matrix; returns LAPACK info.  uplo = 'L' (ChamLower, the one the reference calls): A = L L^T,
+    storage position (i, j), i >= j, holds tile (i, j).  uplo = 'U' (ChamUpper): A = U^T U, and storage position
+    (i, j), i >= j, holds the UPPER tile (j, i) (block row j, block column i) of A on entry and of U on exit;
+    only the upper triangle of the diagonal tiles is referenced.  Since U = L^T, the upper case transposes
+    every tile in place, runs the lower factorization and transposes back (two sweeps over the matrix at HBM
+    speed next to N^3/3 flops)."""
+    if uplo in ("U", "u"):
+        if A.device.type != "cuda":
+            raise RuntimeError("potrf_tile_desc('U') needs a CUDA device: there is no CPU path")
+        transpose_tiles(A)
+        try:
+            return potrf_tile_desc("L", A, group=group, lookahead=lookahead)
+        finally:
+            transpose_tiles(A)
     if uplo not in ("L", "l"):
-        raise ValueError("only uplo='L' (ChamLower) is supported")
+        raise ValueError("uplo must be 'L' (ChamLower) or 'U' (ChamUpper)")
     # one plan (and, on several ranks, one set of communicators / peer buffers) per descriptor storage:
     # repeated calls on the same matrix must not create new process groups every time
     key = (A.desc, A.rank, A.buf.data_ptr(), lookahead, id(group))
@@ -712,6 +724,13 @@ def potrf_tile_desc(uplo: str, A: TileMatrix, group=None, lookahead: bool = True
         ch = _plans[key] = TiledCholesky(A, group=group, lookahead=lookahead)
     ch.factor()
     return ch.info()
+
+
+def transpose_tiles(A: TileMatrix) -> None:
+    """Transpose every local tile of A in place (asynchronous on the current stream)."""
+    b = A.b
+    st = torch.cuda.current_stream(A.device).cuda_stream
+    _lib.call("chol_tile_transpose", b, A.buf.data_ptr(), b, b * b, A.buf.shape[0], st)
 
 
 _plans: dict = {}

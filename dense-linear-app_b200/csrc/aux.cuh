@@ -120,6 +120,34 @@ __global__ void tile_tril_kernel(int n, const double* __restrict__ A, int lda, d
     B[size_t(j) * ldb + i] = (i >= j) ? A[size_t(j) * lda + i] : 0.0;
 }
 
+// In-place transposition of `ntiles` n x n column-major tiles (tile t at A + t * stride): the bridge between
+// uplo = Upper and the lower-triangular kernels (A = U^T U  <=>  A = L L^T with L = U^T).  One CTA per pair
+// of 32 x 32 sub-blocks (I, J), I >= J, of one tile; both are staged in shared memory and written back swapped.
+__global__ void __launch_bounds__(256) tile_transpose_kernel(int n, double* __restrict__ A, int lda, long long stride) {
+    __shared__ double sa[32][33], sb[32][33];
+    const int nb = (n + 31) / 32;
+    int I = 0;
+    while ((I + 1) * (I + 2) / 2 <= int(blockIdx.x)) ++I;
+    const int J = int(blockIdx.x) - I * (I + 1) / 2;
+    if (I >= nb) return;
+    double* T = A + size_t(blockIdx.y) * size_t(stride);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int c = ty; c < 32; c += 8) {
+        const int ra = I * 32 + tx, ca = J * 32 + c;             // block (I, J): rows I, columns J
+        if (ra < n && ca < n) sa[c][tx] = T[size_t(ca) * lda + ra];
+        const int rb = J * 32 + tx, cb = I * 32 + c;             // block (J, I)
+        if (I != J && rb < n && cb < n) sb[c][tx] = T[size_t(cb) * lda + rb];
+    }
+    __syncthreads();
+    for (int c = ty; c < 32; c += 8) {
+        // new (J, I)[r][c'] = old (I, J)[c'][r]
+        const int rb = J * 32 + tx, cb = I * 32 + c;
+        if (rb < n && cb < n) T[size_t(cb) * lda + rb] = sa[tx][c];
+        const int ra = I * 32 + tx, ca = J * 32 + c;
+        if (I != J && ra < n && ca < n) T[size_t(ca) * lda + ra] = sb[tx][c];
+    }
+}
+
 // ---- FP64 peak microbenchmarks -------------------------------------------------------
 // kind 0: 16 independent DFMA chains per thread.
 __global__ void __launch_bounds__(1024, 1) peak_dfma_kernel(int iters, double* out) {

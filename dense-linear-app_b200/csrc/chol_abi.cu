@@ -498,6 +498,24 @@ int chol_tile_tril(int n, const double* A, int lda, double* B, int ldb, void* st
     return 0;
 }
 
+int chol_tile_transpose(int n, double* A, int lda, long long stride, int ntiles, void* stream) {
+    if (n < 0) return fail_arg(1, "chol_tile_transpose", "n");
+    if (ntiles < 0) return fail_arg(5, "chol_tile_transpose", "ntiles");
+    if (n == 0 || ntiles == 0) return 0;
+    if (!A) return fail_arg(2, "chol_tile_transpose", "A");
+    if (lda < n) return fail_arg(3, "chol_tile_transpose", "lda");
+    if (ntiles > 1 && stride < (long long)lda * n) return fail_arg(4, "chol_tile_transpose", "stride");
+    if (int rc = ensure_init()) return rc;
+    const int nb = (n + 31) / 32;
+    for (int t0 = 0; t0 < ntiles; t0 += 65535) {
+        const int cnt = (ntiles - t0 < 65535) ? ntiles - t0 : 65535;
+        tile_transpose_kernel<<<dim3(nb * (nb + 1) / 2, cnt), 256, 0, (cudaStream_t)stream>>>(
+            n, A + size_t(t0) * size_t(stride), lda, stride);
+        CHECK_LAUNCH("tile_transpose_kernel");
+    }
+    return 0;
+}
+
 int chol_fp64_peak(int kind, int iters, double* flops_out, void* stream) {
     if (!flops_out) return fail_arg(3, "chol_fp64_peak", "flops_out");
     if (int rc = ensure_init()) return rc;

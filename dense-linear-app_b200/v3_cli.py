@@ -112,13 +112,14 @@ def main(argv: list[str] | None = None) -> int:
     if a["dtyp"] != "d":
         sys.stderr.write("Error: only --dtyp d runs (the reference calls the d routines for every type).\n")
         return 1
-    if a["uplo"] != "L":
-        sys.stderr.write("Error: only --uplo L (ChamLower) is supported.\n")
+    if a["uplo"] not in ("L", "U"):
+        # ChamUpperLower makes no sense for a Cholesky factorization (Chameleon returns -1 for it)
+        sys.stderr.write("Error: --uplo must be L (ChamLower) or U (ChamUpper) for dpotrf.\n")
         return 1
 
     import torch
     from . import runtime
-    from .cholesky import TiledCholesky
+    from .cholesky import TiledCholesky, transpose_tiles
     from .tiles import TileDesc, TileMatrix
 
     rank, world = runtime.init(a["ncpu"], a["ngpu"])
@@ -135,9 +136,17 @@ def main(argv: list[str] | None = None) -> int:
     if world > 1:
         torch.distributed.barrier()
     # task submission (the plan) is part of CHAMELEON_dpotrf_Tile's bracket (v3_script_cholesky_x_arg_gpt.c:224-228)
+    upper = a["uplo"] == "U"
+    if upper:
+        transpose_tiles(A)          # dplgsy(ChamUpper): storage position (i, j) now holds the upper tile (j, i)
+        torch.cuda.synchronize()
     t0 = time.monotonic()
+    if upper:
+        transpose_tiles(A)          # A = U^T U as the lower factorization of the transposed tiles (cholesky.py)
     ch = TiledCholesky(A)
     ch.factor()
+    if upper:
+        transpose_tiles(A)
     info = ch.info()
     time_sec = time.monotonic() - t0
     dim = float(min(a["m"], a["n"]))

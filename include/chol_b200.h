@@ -207,6 +207,10 @@ int chol_tile_abs_sums(int m, int n, const double* A, int lda, int mode, double*
                        double* d_cols, void* stream);
 /* B <- lower triangle of A, strict upper zeroed (dlacpy(ChamLower), V6:77). */
 int chol_tile_tril(int n, const double* A, int lda, double* B, int ldb, void* stream);
+/* In-place transposition of ntiles n x n column-major tiles, tile t at A + t*stride doubles.  The bridge for
+ * uplo = Upper (cham_uplo_t of CHAMELEON_dpotrf_Tile, V6:56; `--uplo U` of v3_script_cholesky_x_arg_gpt.c:36-44):
+ * A = U^T U is the lower factorization of the transposed tiles, U(j,i) = L(i,j)^T. */
+int chol_tile_transpose(int n, double* A, int lda, long long stride, int ntiles, void* stream);
 
 /* ---- SM partition for the latency-critical panel chain -------------------------------- */
 

@@ -88,8 +88,10 @@ def test_potrf_tile_desc_entry_point_and_info(cuda_lib, oracle):
     assert potrf_tile_desc("L", TileMatrix(TileDesc.square(N, b)).from_numpy(A)) == 0
     A[300, 300] = -4.0
     assert potrf_tile_desc("L", TileMatrix(TileDesc.square(N, b)).from_numpy(A)) == 301   # global LAPACK index
+    # uplo = 'U' on the same (symmetric) input: the bad pivot is found at the same index
+    assert potrf_tile_desc("U", TileMatrix(TileDesc.square(N, b)).from_numpy(A)) == 301
     with pytest.raises(ValueError):
-        potrf_tile_desc("U", TileMatrix(TileDesc.square(N, b)).from_numpy(A))
+        potrf_tile_desc("B", TileMatrix(TileDesc.square(N, b)).from_numpy(A))   # ChamUpperLower: not a Cholesky
 
 
 def test_strict_upper_of_diagonal_tiles_untouched(cuda_lib, oracle):
@@ -262,6 +264,33 @@ def test_potrf_batched_strided_through_the_c_abi(cuda_lib, oracle, n, lda, pad):
         assert np.array_equal(np.triu(got, 1), np.triu(m, 1))
         assert np.all(blk[:, n:] == -7.5)
         assert np.all(out[i * stride + lda * n:(i + 1) * stride] == -7.5)
+
+
+@pytest.mark.parametrize("N,b", [(1024, 256), (1000, 128)])
+def test_potrf_tile_desc_upper_is_the_transposed_lower_factor(cuda_lib, N, b):
+    """uplo = 'U' (ChamUpper of CHAMELEON_dpotrf_Tile, v6_test.c:56; --uplo U of the v3 driver): storage
+    position (i, j) holds the upper tile (j, i); the result must be U(j, i) = L(i, j)^T bit for bit, and the
+    strict LOWER triangle of the diagonal tiles must not be touched."""
+    from dense_linear_app_b200.cholesky import potrf_tile_desc, transpose_tiles
+    from dense_linear_app_b200.tiles import TileDesc, TileMatrix
+    AL = TileMatrix(TileDesc.square(N, b)).generate(float(N), 3)
+    AU = AL.clone()
+    transpose_tiles(AU)                                  # now the upper tiles
+    nt = AL.nt
+    for k in range(nt):                                  # sentinel in the strict lower triangle of the diagonal tiles
+        t = AU.tile(k, k)                                # torch view [col][row]: strict lower = row > col = triu(t, 1)
+        t += torch.triu(torch.full_like(t, 123.0), 1)
+    assert potrf_tile_desc("L", AL) == 0
+    assert potrf_tile_desc("U", AU) == 0
+    torch.cuda.synchronize()
+    for i, j in AL.layout.tiles():
+        l, u = AL.tile(i, j), AU.tile(i, j)
+        if i == j:
+            assert torch.equal(torch.tril(u), torch.triu(l).T.contiguous())      # upper triangle of U = (lower of L)^T
+            strict = torch.triu(torch.ones_like(u, dtype=torch.bool), 1)
+            assert bool((u[strict] >= 100.0).all())                               # sentinel region untouched
+        else:
+            assert torch.equal(u, l.T.contiguous())
 
 
 def test_potrf_batched_from_host_matches_device_path(cuda_lib, oracle):

@@ -242,6 +242,55 @@ def test_trsm_panel_form_matches_single_tile_op(cuda_lib, oracle, b, m):
     assert torch.equal(panel, single), "panel form and single-tile form must agree bit for bit"
 
 
+@pytest.mark.parametrize("b,m", [(128, 3), (512, 5), (1024, 2)])
+def test_trsm_panel_fused_push_writes_the_peers_slots(cuda_lib, b, m):
+    """chol_trsm_tiles_push = chol_trsm_tiles + the same result stored, by the solving kernel itself, into up to
+    seven peers' receive slots.  Here the "peers" are two more buffers on the same GPU (a peer mapping is just an
+    address): both copies must equal the tiles bit for bit, a null entry must leave that slot untouched, and the
+    tiles must be what chol_trsm_tiles produces."""
+    from dense_linear_app_b200 import _lib
+    lib = _lib.load()
+    Ai, _, _ = tiles(b, 900 + b)
+    S = np.asfortranarray(Ai @ Ai.T + b * np.eye(b))
+    dS = dev_cm(S)
+    work = torch.empty(max(lib.chol_potrf_tile_workspace(b) // 8, 1), dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("chol_potrf_tile", b, dS.data_ptr(), b, work.data_ptr(), info.data_ptr(), 0, st)
+    panel = torch.rand(m, b, b, dtype=torch.float64, device="cuda") - 0.5
+    plain = panel.clone()
+    slots = torch.full((2, m, b, b), -7.5, dtype=torch.float64, device="cuda")
+    ptrs = torch.tensor([panel[i].data_ptr() for i in range(m)], dtype=torch.int64, device="cuda")
+    pptrs = torch.tensor([plain[i].data_ptr() for i in range(m)], dtype=torch.int64, device="cuda")
+    dst = [[slots[q, i].data_ptr() for q in range(2)] for i in range(m)]
+    dst[m - 1][1] = 0                                   # peer 1 does not read the last tile
+    d_dst = torch.tensor(dst, dtype=torch.int64, device="cuda")
+    _lib.call("chol_trsm_tiles_push", b, dS.data_ptr(), b, work.data_ptr(), ptrs.data_ptr(), m, b, d_dst.data_ptr(), 2, st)
+    _lib.call("chol_trsm_tiles", b, dS.data_ptr(), b, work.data_ptr(), pptrs.data_ptr(), m, b, None, st)
+    torch.cuda.synchronize()
+    assert torch.equal(panel, plain)
+    assert torch.equal(slots[0], panel)
+    assert torch.equal(slots[1, :m - 1], panel[:m - 1])
+    assert bool((slots[1, m - 1] == -7.5).all())
+
+
+@pytest.mark.parametrize("n,lda,ntiles", [(1, 1, 1), (5, 8, 3), (32, 32, 2), (100, 128, 4), (256, 256, 3)])
+def test_tile_transpose_in_place(cuda_lib, n, lda, ntiles):
+    from dense_linear_app_b200 import _lib
+    st = torch.cuda.current_stream().cuda_stream
+    stride = lda * n + 6
+    buf = torch.rand(ntiles * stride, dtype=torch.float64, device="cuda")
+    ref = buf.clone()
+    _lib.call("chol_tile_transpose", n, buf.data_ptr(), lda, stride, ntiles, st)
+    torch.cuda.synchronize()
+    for t in range(ntiles):
+        got = buf[t * stride:t * stride + lda * n].reshape(n, lda)          # [column][row]
+        old = ref[t * stride:t * stride + lda * n].reshape(n, lda)
+        assert torch.equal(got[:, :n], old[:, :n].T.contiguous())
+        assert torch.equal(got[:, n:], old[:, n:])                           # padding rows untouched
+        assert torch.equal(buf[t * stride + lda * n:(t + 1) * stride], ref[t * stride + lda * n:(t + 1) * stride])
+
+
 @pytest.mark.parametrize("m,n", [(1, 1), (5, 3), (64, 64), (200, 130), (512, 512)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_norm_building_blocks(cuda_lib, m, n, mode):

@@ -282,4 +282,4 @@ def test_v3_named_argument_cli_checks():
     assert code is None and "bump==0" in msg
     assert run(with_("uplo", "u"))[1]["uplo"] == "U" and run(with_("dtyp", "2"))[1]["dtyp"] == "z"
     # unsupported-but-valid choices are refused before any CUDA work
-    assert v3_cli.main(["v3"] + with_("uplo", "U")) == 1 and v3_cli.main(["v3"] + with_("dtyp", "s")) == 1
+    assert v3_cli.main(["v3"] + with_("uplo", "B")) == 1 and v3_cli.main(["v3"] + with_("dtyp", "s")) == 1
