@@ -603,8 +603,9 @@ def main_ours(a) -> int:
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "launches_timed": len(upd), "share_of_step": upd_s / elapsed if elapsed else None,
                          "traffic": traffic, "traffic_note": traffic_note,
-                         "traffic_config": "one ncu --set full capture of ONE part-b update launch at N=16384, "
-                                           "tile 1024 (profiles/), not of the benched configuration"}}
+                         "traffic_config": "one ncu --set full capture of ONE 120-task update launch (15-tile panel, "
+                                           "tile 1024; profiles/r02_update_kernel_ncu.md), per launch like "
+                                           "`achieved`; not a capture of the benched run"}}
     if not a.no_cpu_baseline and world == 1:
         try:
             cores = host_cores()

@@ -115,9 +115,12 @@ class TiledCholesky:
         once the bulk of a step's update has at most `tail_tasks` tile tasks, the panel chain bounds the
         step; from then on the updates run on the `rest` group of SMs and POTRF on its private group, so
         none of its ~24 short dependent kernels waits for an update CTA to retire (measured on B200: a
-        POTRF tile takes 0.55 ms alone and 1.3-1.5 ms under a running update).  CHOL_PANEL_SMS=0 turns it
-        off; a driver without green contexts leaves the ordinary two-stream schedule."""
-        sms = int(os.environ.get("CHOL_PANEL_SMS", "16"))
+        POTRF tile takes 0.6 ms alone, 1.3-1.5 ms under a running update, 0.74 ms on its own 16 SMs;
+        N=16384: 51.9 -> 51.1 ms, 8 GPUs N=65536: 393.5 -> 390.1 ms).
+        OPT-IN (CHOL_PANEL_SMS=16): a process that uses green contexts is killed by Nsight Compute 2025.2
+        (observed: exit status 9 at the first launch on a green-context stream), and a 1 % gain does not
+        justify a default that cannot be profiled."""
+        sms = int(os.environ.get("CHOL_PANEL_SMS", "0"))
         self.tail_tasks = int(os.environ.get("CHOL_TAIL_TASKS", "28" if self.world == 1 else "48"))
         if sms <= 0 or self.tail_tasks <= 0 or self.nt < 3:
             return
