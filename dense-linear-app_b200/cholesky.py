@@ -39,6 +39,9 @@ class TiledCholesky:
     tr = None
     thin_tasks = 0
     _potrf_on_partition = False
+    lazy_steps = 1
+    lazy_index = None
+    d_lazy = None
     s_potrf = None      # streams of the SM partition (chol_partition_create), None = no partition
     s_rest = None
     tail_tasks = 0
@@ -280,6 +283,7 @@ class TiledCholesky:
         self.d_trsm_ptrs = torch.from_numpy(tptr).to(self.dev)
         self.n_update_tasks = off
         self.step0_head, self.step0_groups = self._step0_groups()
+        self._build_lazy_plan()
 
     def _step0_groups(self, ngroups: int = 8):
         """Upload/compute pipeline of factor_from_host for step 0.  Returns (head_hi, groups): local
@@ -302,6 +306,41 @@ class TiledCholesky:
                     t0 += nxt - lo
                     lo = nxt
         return head_hi, groups
+
+    def _build_lazy_plan(self, max_steps: int = 4) -> None:
+        """Host-resident input on one rank (factor_from_host): the upload of a large matrix takes longer than
+        step 0's update (N=65536 over PCIe: 0.32 s against 0.13 s), and a right-looking step touches every
+        column, so step 1 would wait for the last tile.  The first S steps are therefore applied LAZILY: while
+        the later column groups are still arriving, steps 0..S-1 run on the columns that are already there
+        (the head and upload group 0, which hold every column <= S: all their panels and the first panel after
+        them); each later group receives its updates 0..S-1, in that order, as soon as it has arrived; from
+        step S on everything is as usual.  Every tile still sees its updates in the same order, one launch per
+        step, so the factor is bit-identical.  Here: the part-b tasks of steps 1..S-1 cut by upload group."""
+        self.lazy_steps, self.lazy_index, self.d_lazy = 1, {}, None
+        if self.world != 1 or len(self.step0_groups) < 2:
+            return
+        lay, tb, base = self.lay, self.tile_bytes, self.A.buf.data_ptr()
+        hi0 = self.step0_groups[0][3]                      # tiles [0, hi0): head + group 0
+        last_col = max((j for j in lay.cols if lay.col_start[j] < hi0 and
+                        (lay.col_start[j] + len(lay.rows_in_col(j, j - 1))) <= hi0), default=0)
+        S = min(max_steps, last_col, self.nt - 2)
+        if S < 2:
+            return
+        bounds = [(g[2], g[3]) for g in self.step0_groups]
+        bounds[0] = (self.step0_head, bounds[0][1])
+        recs, off = [], 0
+        for k in range(1, S):
+            o, nd, na, ntot = self.step_tasks[k]
+            part_b = self.tasks_host[o + na:o + ntot]
+            tile = (part_b[:, 0] - base) // tb
+            for g, (lo, hi) in enumerate(bounds):
+                sel = part_b[(tile >= lo) & (tile < hi)]
+                self.lazy_index[(k, g)] = (off, sel.shape[0])
+                recs.append(sel)
+                off += sel.shape[0]
+            assert sum(self.lazy_index[(k, g)][1] for g in range(len(bounds))) == ntot - na
+        self.lazy_steps = S
+        self.d_lazy = torch.from_numpy(np.concatenate(recs) if off else np.zeros((1, 4), dtype=np.int64)).to(self.dev)
 
     def _make_column_groups(self) -> None:
         import torch.distributed as dist
@@ -479,6 +518,19 @@ class TiledCholesky:
                 continue
             with torch.cuda.stream(su):
                 gated = k == 0 and bool(step0_gates)
+                lazy = bool(step0_gates) and factor and self.lookahead and self.lazy_steps > 1
+                if lazy and k == self.lazy_steps:
+                    # the later upload groups catch up: updates 0 .. S-1, in order, group by group as they arrive
+                    for g in range(1, len(self.step0_groups)):
+                        su.wait_event(step0_gates[1 + g])
+                        t0, t1, _, _ = self.step0_groups[g]
+                        o0, _, na0, _ = self.step_tasks[0]
+                        if t1 > t0:
+                            self._k_update(update_tasks_ptr + (o0 + na0 + t0) * 32, t1 - t0, st)
+                        for kk in range(1, self.lazy_steps):
+                            lo_, cnt_ = self.lazy_index[(kk, g)]
+                            if cnt_:
+                                self._k_update(self.d_lazy.data_ptr() + lo_ * 32, cnt_, st)
                 if gated:
                     for ev in (step0_gates if not self.lookahead else step0_gates[:1]):
                         su.wait_event(ev)
@@ -503,10 +555,15 @@ class TiledCholesky:
                     ev_col = self._record()
                     self._mark("upd_a", k, su)
                 if gated:
-                    # host-resident input: release part b group by group behind the upload
-                    for g, (t0, t1, _, _) in enumerate(self.step0_groups):
+                    # host-resident input: release part b group by group behind the upload (lazy first steps:
+                    # only the first group now, the others catch up before step S)
+                    for g, (t0, t1, _, _) in enumerate(self.step0_groups[:1] if lazy else self.step0_groups):
                         su.wait_event(step0_gates[1 + g])
                         self._k_update(base + (na + t0) * 32, t1 - t0, st)
+                elif lazy and k < self.lazy_steps:
+                    lo_, cnt_ = self.lazy_index[(k, 0)]
+                    if cnt_:
+                        self._k_update(self.d_lazy.data_ptr() + lo_ * 32, cnt_, st)
                 elif ntot > na:
                     # the bulk of the update overlaps panel step k+1: once it is small enough for that panel
                     # chain to bound the step, it runs at one CTA per SM and leaves the chain's kernels room

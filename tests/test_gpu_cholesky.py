@@ -422,10 +422,11 @@ def test_v6_test_command_line(cuda_lib):
     assert "PASS" in pr.stdout
 
 
-@pytest.mark.parametrize("N,b", [(256, 128), (1024, 128), (2048, 256), (1000, 128)])
+@pytest.mark.parametrize("N,b", [(256, 128), (1024, 128), (2048, 256), (1000, 128), (4096, 128), (3072, 64)])
 def test_factor_from_host_matches_device_path(cuda_lib, oracle, N, b):
-    """End-to-end entry (pinned host tiles -> H2D pipelined under step 0 -> factor -> D2H of each
-    finished column): bit-identical to the device-resident path, input buffer left untouched."""
+    """End-to-end entry (pinned host tiles -> H2D pipelined under the first steps, which are applied lazily to
+    the column groups as they arrive -> factor -> D2H of each finished column): bit-identical to the
+    device-resident path, input buffer left untouched."""
     from dense_linear_app_b200.cholesky import TiledCholesky
     from dense_linear_app_b200.tiles import TileDesc, TileMatrix
     M = TileMatrix(TileDesc.square(N, b)).generate(float(N), 3)
@@ -438,6 +439,8 @@ def test_factor_from_host_matches_device_path(cuda_lib, oracle, N, b):
     hin.copy_(pristine)
     hout = torch.zeros(M.buf.shape, dtype=torch.float64).pin_memory()
     M.buf.zero_()                                   # the device buffer must be filled by the upload
+    if N // b >= 16:
+        assert ch.lazy_steps >= 2                   # the lazy first steps are what is being tested
     for _ in range(2):                              # twice: stream/event reuse across calls
         ch.factor_from_host(hin, hout)
         torch.cuda.synchronize()

@@ -309,3 +309,15 @@ def test_factor_from_host_schedule_has_no_races(fake_cuda, monkeypatch, P, Q, ra
         first_upd = next(o for o in pr.ops if o[0] == "update")
         last_up = [o for o in pr.ops if o[0] == "h2d"][-1]
         assert not happens_before(last_up, first_upd)
+        if P * Q == 1:
+            # lazy first steps: the panel chain gets S steps deep without waiting for the last upload group,
+            # and step S (which touches every column) does wait for it
+            S = pr.lazy_steps
+            assert S >= 2
+            n_up = sum(1 for o in pr.ops if o[0] == "h2d") // 2          # uploads of one call
+            first_call = pr.ops[:next(i for i, o in enumerate(pr.ops) if o[0] == "h2d" and
+                                      sum(1 for q in pr.ops[:i + 1] if q[0] == "h2d") > n_up)]
+            pot = [o for o in first_call if o[0] == "potrf"]
+            last_up1 = [o for o in first_call if o[0] == "h2d"][-1]
+            assert not happens_before(last_up1, pot[S - 1])
+            assert happens_before(last_up1, pot[S + 1])
