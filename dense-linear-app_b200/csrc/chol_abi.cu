@@ -27,6 +27,7 @@ std::mutex g_mu;
 bool g_force_wide = false;  // CHOL_GEMM_WIDE=1: use the 128x128 shape everywhere (A/B experiments)
 bool g_inited[64] = {false};
 bool g_panel_v1 = false;    // CHOL_PANEL_V1=1: round-1 panel kernels (full 128x128 inverses) for every tile size
+bool g_pdl = true;          // CHOL_PDL=0: no programmatic dependent launch for the panel chain
 int g_batched_ll = 4;       // CHOL_BATCHED_LL: 4 = left-looking DMMA kernel, 4 stages x 4 CTAs/SM (default);
                             // 6 = 6 stages x 3 CTAs/SM; 0 = round-1 kernels (A/B experiments)
 
@@ -72,6 +73,7 @@ int ensure_init() {
                          cudaSharedmemCarveoutMaxShared);
     if (const char* w = getenv("CHOL_BATCHED_LL")) g_batched_ll = atoi(w);
     if (const char* w = getenv("CHOL_PANEL_V1")) g_panel_v1 = (w[0] == '1');
+    if (const char* w = getenv("CHOL_PDL")) g_pdl = (w[0] != '0');
     e = cudaFuncSetAttribute(potrf_diag32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(D2_SMEM));
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_diag32_kernel)");
     e = cudaFuncSetAttribute(trsm_leaf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LF_SMEM));
@@ -86,6 +88,30 @@ int ensure_init() {
 namespace {
 
 constexpr size_t GEMM_THIN_SMEM = 120 * 1024;
+
+// Programmatic dependent launch for the kernels of the panel chain (see pdl_sync in gemm_dmma.cuh): set by
+// chol_potrf_tile / the TRSM sweep around their launches.  CHOL_PDL=0 turns it off.
+thread_local bool t_chain = false;
+struct ChainScope {
+    bool prev;
+    ChainScope() : prev(t_chain) { t_chain = g_pdl; }
+    ~ChainScope() { t_chain = prev; }
+};
+
+template <class... KArgs, class... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = t_chain ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -122,12 +148,12 @@ int launch_gemm(GemmParams p, cudaStream_t st, bool inplace_tri = false, bool th
         const long long grid = (long long)ntasks * p.nbm * p.nbn;
         if (grid > 0x7fffffffLL) return fail_arg(2, "chol_gemm_tasks", "too many CTA tiles");
         if (wide)
-            gemm_nt_dmma_kernel<GemmWide><<<dim3((unsigned)grid), GemmWide::THREADS, GemmWide::SMEM_BYTES, st>>>(p);
+            launch_k(gemm_nt_dmma_kernel<GemmWide>, dim3((unsigned)grid), dim3(GemmWide::THREADS), GemmWide::SMEM_BYTES, st, p);
         else
             // `thin`: ask for more dynamic shared memory than the kernel uses so that only ONE CTA fits per SM and
             // the other half of every SM stays free for the panel kernels of the next step
-            gemm_nt_dmma_kernel<GemmPair><<<dim3((unsigned)grid), GemmPair::THREADS,
-                                            thin ? GEMM_THIN_SMEM : GemmPair::SMEM_BYTES, st>>>(p);
+            launch_k(gemm_nt_dmma_kernel<GemmPair>, dim3((unsigned)grid), dim3(GemmPair::THREADS),
+                     thin ? GEMM_THIN_SMEM : size_t(GemmPair::SMEM_BYTES), st, p);
         CHECK_LAUNCH("gemm_nt_dmma_kernel");
         return 0;
     }
@@ -173,7 +199,7 @@ int launch_leaf(double* const* d_tiles, double* single, int ntiles, long long of
     p.ctas_per_task = (m + LF_ROWS - 1) / LF_ROWS;
     const long long grid = (long long)ntiles * p.ctas_per_task;
     if (grid > 0x7fffffffLL) return fail_arg(6, "chol_trsm_tiles", "too many CTAs");
-    trsm_leaf32_kernel<<<dim3((unsigned)grid), LF_THREADS, LF_SMEM, st>>>(p);
+    launch_k(trsm_leaf32_kernel, dim3((unsigned)grid), dim3(LF_THREADS), LF_SMEM, st, p);
     CHECK_LAUNCH("trsm_leaf32_kernel");
     return 0;
 }
@@ -235,6 +261,7 @@ int trsm_sweep(int b, const double* L, int ldl, const double* Winv, double* cons
     const bool v2 = fast32(b, lda, ldl, single ? (const void*)single : (const void*)L, L) && aligned16(Winv);
     if (peer_dst && !v2) return fail_arg(1, "chol_trsm_tiles_push", "the fused push needs tiles that are multiples of 32");
     TrsmCtx c{b, L, ldl, Winv, d_tiles, single, ntiles, lda, st, v2, peer_dst, npeer};
+    ChainScope chain;
     return trsm_rec(c, 0, (b + NBD - 1) / NBD);
 }
 
@@ -298,6 +325,7 @@ int chol_potrf_tile(int b, double* A, int lda, double* work, int* d_info, int in
     cudaStream_t st = (cudaStream_t)stream;
     const int nblk = (b + NBD - 1) / NBD;
     const bool v2 = fast32(b, lda, lda, A, A) && aligned16(work);
+    ChainScope chain;
     for (int j = 0; j < nblk; ++j) {
         const int o = j * NBD;
         const int nbv = (b - o < NBD) ? b - o : NBD;
@@ -305,7 +333,7 @@ int chol_potrf_tile(int b, double* A, int lda, double* work, int* d_info, int in
         double* Wj = work + size_t(j) * NBD * NBD;
         double* Ajj = A + size_t(o) * lda + o;
         if (v2) {
-            potrf_diag32_kernel<<<1, D2_THREADS, D2_SMEM, st>>>(nbv, Ajj, lda, Wj, d_info, info_base + o);
+            launch_k(potrf_diag32_kernel, dim3(1), dim3(D2_THREADS), D2_SMEM, st, nbv, Ajj, lda, Wj, d_info, info_base + o);
             CHECK_LAUNCH("potrf_diag32_kernel");
         } else {
             potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(nbv, Ajj, lda, Wj, d_info, info_base + o);

@@ -115,6 +115,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// Programmatic dependent launch (the latency-bound panel chain: 24 dependent launches per POTRF tile, 15 per panel
+// TRSM).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its
+// predecessor in the stream is still running; it must call this before it touches anything the predecessor wrote.
+// The trigger for ITS successor comes right after the wait, so at most one successor is resident early (a trigger
+// at the very top would let the whole chain pile up on the SMs).  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 // TMA engine 1-D bulk copy shared -> global (bulk async-group completion).
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
@@ -211,6 +220,8 @@ gemm_nt_dmma_kernel(const __grid_constant__ GemmParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+
+    pdl_sync();      // (the task records above are plan data, never written by a predecessor kernel)
 
     // The host checks the 16-byte alignment the bulk copies and the 16-byte C accesses need only for a
     // single task; the pointers of a device task list / tile list are checked here, per task.  A task

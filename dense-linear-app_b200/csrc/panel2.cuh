@@ -63,6 +63,7 @@ potrf_diag32_kernel(int n, double* __restrict__ A, int lda, double* __restrict__
     {
         const uint32_t bar = smem_u32(&s_bar);
         const int ncols = nb * (nb + 1) / 2 * SB;
+        pdl_sync();
         if (tid == 0) {
             mbar_init(bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(LF_THREADS, 2) trsm_leaf32_kernel(const __grid
     const int rb = blockIdx.x - task * p.ctas_per_task;
     double* Abase = (p.tile_ptrs ? p.tile_ptrs[task] : p.single) + p.off;
     const int nbk = p.nbk;
+    pdl_sync();      // (the tile-pointer list is plan data)
     if ((reinterpret_cast<uintptr_t>(Abase) & 15u) != 0) {
         // a tile of the pointer list that is only 8-byte aligned (the host cannot see device pointer lists):
         // plain forward substitution, one thread per row — slow, correct, and no misaligned 16-byte access
