@@ -92,3 +92,37 @@ def test_tilematrix_roundtrip_and_identity_padding():
     last = M.tile(3, 3).numpy().T                         # column-major view of the ragged diagonal tile
     assert np.array_equal(last[2:, 2:], np.eye(14)) and not last[2:, :2].any()
     assert M.clone().buf.data_ptr() != M.buf.data_ptr()
+
+
+@pytest.mark.parametrize("N,b", [(16 * 9, 16), (16 * 24, 16), (16 * 64, 16), (16 * 3, 16)])
+def test_lazy_plan_of_the_host_resident_path(N, b):
+    """factor_from_host on one rank applies the first S steps lazily per upload group (cholesky._build_lazy_plan):
+    the part-b tasks of steps 1..S-1 are cut by upload group without loss or duplication, and everything the panel
+    chain of those steps needs (columns <= S) is in the head or in group 0."""
+    M = TileMatrix(TileDesc.square(N, b), 0, "cpu")
+    pl = PlanOnly(M)
+    nt, S = M.nt, pl.lazy_steps
+    base, tb = M.buf.data_ptr(), M.tile_bytes
+    if nt < 6:
+        assert S == 1 and pl.d_lazy is None            # too small: nothing to do lazily
+        return
+    assert 2 <= S <= 4
+    lazy = pl.d_lazy.numpy()
+    bounds = [(g[2], g[3]) for g in pl.step0_groups]
+    ptr2tile = {base + M.layout.index(i, j) * tb: (i, j) for i, j in M.layout.tiles()}
+    early_hi = bounds[0][1]
+    for j in range(S + 1):                              # every column <= S is on the device before group 1 arrives
+        assert M.layout.index(nt - 1, j) < early_hi
+    for k in range(1, S):
+        off, nd, na, ntot = pl.step_tasks[k]
+        want = {tuple(r) for r in pl.tasks_host[off + na:off + ntot].tolist()}
+        got = []
+        for g, (lo, hi) in enumerate(bounds):
+            o, cnt = pl.lazy_index[(k, g)]
+            for c, a, bb, flag in lazy[o:o + cnt].tolist():
+                t = (c - base) // tb
+                assert lo <= t < hi                     # the task's C tile belongs to this upload group
+                i, j = ptr2tile[c]
+                assert j >= k + 2                       # part b only: column k+1 is part a
+                got.append((c, a, bb, flag))
+        assert len(got) == len(want) and set(got) == want
