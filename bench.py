@@ -320,7 +320,7 @@ def measure_batched(batch: int, n: int, steps: int, warmup: int, with_e2e: bool)
     out = {"value": flops / t / 1e12, "unit": UNIT, "ms_per_step": t * 1e3, "ms_best": min(ms), "steps": steps,
            "matrices_per_s": batch / t, "nonzero_info": int((info != 0).sum().item()), "max_backward_error": err,
            "gpu_launches": int(launches),
-           "roofline": {"bound": "hbm", "kernel": "potrf_batched_ll_kernel (left-looking, DMMA, one CTA per matrix)",
+           "roofline": {"bound": "hbm", "kernel": "potrf_batched_np_kernel (left-looking, DMMA, one CTA per matrix, 4 CTAs/SM)",
                         "achieved": alg_bytes / t / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": alg_bytes / t / 1e9 / peak, "peak_source": src, "traffic": None,
                         "algorithmic_bytes": alg_bytes, "also_fp64": "flops / t vs the FP64 DMMA peak: see frac_of_fp64_peak"}}

@@ -118,13 +118,14 @@ potrf_batched_global_kernel(int n, double* __restrict__ Abase, int lda, long lon
 // twice, bit-identical results) was built and measured: faster for a single matrix (n = 224: 135 against
 // 145 us) but slower at the full batch (5.14 against 4.73 ms) — the second visit re-streams the B rows and
 // re-reads/re-writes C, and under four co-resident CTAs that extra L2 traffic costs more than the overlap
-// gains.  Dropped.  So was a variant WITHOUT the producer warp (the last consumer warp to release a slab refills it;
-// 128-thread CTAs, five per SM, bit-identical): 4.76 against 4.73 ms — ncu shows why: with 740 instead of 592
-// matrices in flight the working set (about 290 KB of touched lines per matrix) overflows the 126 MB L2 further, the
-// L2 hit rate falls from 57 to 48.5 % and the DRAM reads rise from 7.3 to 9.6 GB (minimum: 2.6 GB).  This design is
-// therefore at its optimum around 4 CTAs/SM: fewer matrices in flight starve the pipes (3/SM: 5.56 ms), more spill
-// out of L2.  Getting to the 1.5 ms bound needs the matrix resident on chip while the serial chain of one matrix
-// (8 x potrf32 at 5.6 us + 7 substitutions) is overlapped with the updates of another inside the same CTA.
+// gains.  Dropped.  What did help is dropping the PRODUCER WARP (batched_np.cuh, the default): the last consumer warp
+// to release a slab refills it, a CTA is 128 threads, and four of them per SM may use 128 registers instead of 96 —
+// the 300 bytes of spills per thread (44 M local-memory instructions, 17 % of the kernel's L2 sectors) shrink to
+// 80: 4.43 against 4.73 ms, bit-identical.  FIVE such CTAs per SM at 96 registers: 4.76 ms — with 740 instead of
+// 592 matrices in flight the working set (about 290 KB of touched lines per matrix) overflows the 126 MB L2 further
+// (hit rate 57 -> 48.5 %, DRAM reads 7.3 -> 9.6 GB; minimum 2.6 GB).  Three per SM starve the pipes (5.56 ms).
+// Getting to the 1.5 ms bound needs the matrix resident on chip while the serial chain of one matrix (8 x potrf32 at
+// 5.6 us + 7 substitutions) is overlapped with the updates of another inside the same CTA.
 constexpr int BLW = 32;                 // block-column width
 constexpr int BLK = 8;                  // slab depth
 constexpr int BL_ROWS = 128;            // rows per pass

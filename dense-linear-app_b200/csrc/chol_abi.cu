@@ -9,6 +9,7 @@
 #include "abi_common.cuh"
 #include "aux.cuh"
 #include "batched.cuh"
+#include "batched_np.cuh"
 #include "gemm_dmma.cuh"
 #include "panel.cuh"
 #include "panel2.cuh"
@@ -28,7 +29,8 @@ bool g_force_wide = false;  // CHOL_GEMM_WIDE=1: use the 128x128 shape everywher
 bool g_inited[64] = {false};
 bool g_panel_v1 = false;    // CHOL_PANEL_V1=1: round-1 panel kernels (full 128x128 inverses) for every tile size
 bool g_pdl = true;          // CHOL_PDL=0: no programmatic dependent launch for the panel chain
-int g_batched_ll = 4;       // CHOL_BATCHED_LL: 4 = left-looking DMMA kernel, 4 stages x 4 CTAs/SM (default);
+int g_batched_ll = 5;       // CHOL_BATCHED_LL: 5 = left-looking DMMA kernel without a producer warp, 4 CTAs/SM x 128
+                            // registers (batched_np.cuh, default); 4 = with a producer warp, 4 CTAs/SM x 96 registers;
                             // 6 = 6 stages x 3 CTAs/SM; 0 = round-1 kernels (A/B experiments)
 
 }  // namespace
@@ -70,6 +72,11 @@ int ensure_init() {
     cudaFuncSetAttribute(potrf_batched_ll_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(potrf_batched_ll_kernel<6, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(potrf_batched_np_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(BatchedNP<4>::SMEM));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(potrf_batched_np_kernel<4,4>)");
+    cudaFuncSetAttribute(potrf_batched_np_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     if (const char* w = getenv("CHOL_BATCHED_LL")) g_batched_ll = atoi(w);
     if (const char* w = getenv("CHOL_PANEL_V1")) g_panel_v1 = (w[0] == '1');
@@ -449,7 +456,9 @@ int chol_potrf_batched(int n, int batch, double* A, int lda, long long stride, i
     cudaStream_t st = (cudaStream_t)stream;
     if (g_batched_ll != 0 && n % BLW == 0 && n <= BATCHED_LL_MAX_N && lda % 2 == 0 && stride % 2 == 0 &&
         aligned16(A)) {
-        if (g_batched_ll == 6)
+        if (g_batched_ll == 5)
+            potrf_batched_np_kernel<4, 4><<<batch, NP_THREADS, BatchedNP<4>::SMEM, st>>>(n, A, lda, stride, d_info);
+        else if (g_batched_ll == 6)
             potrf_batched_ll_kernel<6, 3><<<batch, BL_THREADS, BatchedLL<6>::SMEM, st>>>(n, A, lda, stride, d_info);
         else
             potrf_batched_ll_kernel<4, 4><<<batch, BL_THREADS, BatchedLL<4>::SMEM, st>>>(n, A, lda, stride, d_info);
