@@ -317,12 +317,18 @@ def measure_batched(batch: int, n: int, steps: int, warmup: int, with_e2e: bool)
     err = float((torch.linalg.matrix_norm(full - Lt.transpose(1, 2) @ Lt) / torch.linalg.matrix_norm(full)).max().item())
     del Lt, full
     peak, src = hbm_peak()
+    traffic, traffic_note = None, None
+    ncu_json = os.path.join(ROOT, "profiles", "batched_kernel_ncu.json")     # one `ncu --set full` capture, see profiles/
+    if os.path.exists(ncu_json) and batch == 10000 and n == 256:
+        with open(ncu_json) as f:
+            cap = json.load(f)
+        traffic, traffic_note = cap["dram_bytes_read"] + cap["dram_bytes_write"], cap["note"]
     out = {"value": flops / t / 1e12, "unit": UNIT, "ms_per_step": t * 1e3, "ms_best": min(ms), "steps": steps,
            "matrices_per_s": batch / t, "nonzero_info": int((info != 0).sum().item()), "max_backward_error": err,
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "kernel": "potrf_batched_np_kernel (left-looking, DMMA, one CTA per matrix, 4 CTAs/SM)",
                         "achieved": alg_bytes / t / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": alg_bytes / t / 1e9 / peak, "peak_source": src, "traffic": None,
+                        "frac": alg_bytes / t / 1e9 / peak, "peak_source": src, "traffic": traffic, "traffic_note": traffic_note,
                         "algorithmic_bytes": alg_bytes, "also_fp64": "flops / t vs the FP64 DMMA peak: see frac_of_fp64_peak"}}
     if with_e2e:
         hin = torch.empty(A0.shape, dtype=torch.float64).pin_memory()
