@@ -102,8 +102,14 @@ def potrf_batched_from_host(host_in: torch.Tensor, host_out: torch.Tensor, host_
         raise ValueError("potrf_batched_from_host: host tensors must be pinned")
     if host_in.dtype != torch.float64 or host_in.dim() != 3 or host_in.shape[1] != host_in.shape[2]:
         raise ValueError("potrf_batched_from_host: host_in must be float64 [batch, n, n]")
+    if host_out.shape != host_in.shape or host_out.dtype != torch.float64:
+        raise ValueError("potrf_batched_from_host: host_out must have the shape and dtype of host_in")
+    if host_info.dtype != torch.int32 or host_info.numel() < host_in.shape[0]:
+        raise ValueError("potrf_batched_from_host: host_info must be int32 with one entry per matrix")
     dev = device or torch.device("cuda", torch.cuda.current_device())
     batch, n = host_in.shape[0], host_in.shape[1]
+    if batch == 0 or n == 0:
+        return
     per = -(-batch // max(1, chunks))
     key = (dev.index, per, n)
     st = _pipelines.get(key)
